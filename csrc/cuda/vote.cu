@@ -1,0 +1,113 @@
+// K3: majority vote over repetition groups, per parameter tensor, with exact (whole-tensor) equality.
+//
+// Reference semantics (src/master/rep_master.py:154-168): for each group and each parameter tensor run
+// Boyer-Moore over the group's members in order, comparing *whole tensors* with np.array_equal; the
+// surviving candidate's tensor is that group's contribution.
+//
+// Device formulation: pass 1 (`vote_compare_kernel`) streams all P gradient slots once and produces, per
+// (group, tensor), a bitmask of member pairs that differ anywhere (float `!=`, so NaN != NaN and +0 == -0
+// exactly like np.array_equal).  Pass 2 (`vote_resolve_kernel`, one thread per (group, tensor)) replays
+// Boyer-Moore on that pair table and writes the winning worker slot.  The winner table feeds the fused
+// select + SGD + broadcast kernel (aggregate_update.cu).
+#include "common.cuh"
+
+struct VoteArgs {
+  const float* grad_in;           // [P][slot_stride]
+  long long slot_stride;
+  const int* group_table;         // [G][max_r] worker slots, -1 padded
+  int G, max_r;
+  TileView tv;
+  unsigned int* neq_mask;         // [G][ntensors] pair-mismatch bitmask, pair (i<j) -> bit i*max_r + j ... packed below
+};
+
+__device__ __forceinline__ int pair_bit(int i, int j) {   // i < j < 8  -> 0..27
+  return j * (j - 1) / 2 + i;
+}
+
+__global__ void __launch_bounds__(DRC_THREADS) vote_compare_kernel(const __grid_constant__ VoteArgs a) {
+  __shared__ unsigned int s_mask[DRC_MAX_WORKERS];       // one word per group (G <= 32)
+  for (int tile = blockIdx.x; tile < a.tv.ntiles; tile += gridDim.x) {
+    int tensor;
+    const int valid = tile_valid(a.tv, tile, tensor);
+    if (threadIdx.x < a.G) s_mask[threadIdx.x] = 0u;
+    __syncthreads();
+    const long long idx = (long long)tile * DRC_TILE + threadIdx.x * 4;
+    const bool active = (int)threadIdx.x * 4 < valid;     // padding is zero in every slot: skip whole float4s only
+    for (int g = 0; g < a.G; ++g) {
+      float4 v[DRC_MAX_R];
+      int r = 0;
+#pragma unroll
+      for (int k = 0; k < DRC_MAX_R; ++k) {
+        int slot = k < a.max_r ? a.group_table[g * a.max_r + k] : -1;
+        if (slot >= 0) {
+          r = k + 1;
+          if (active) v[k] = ld_f4(reinterpret_cast<const float4*>(a.grad_in + slot * a.slot_stride + idx));
+        }
+      }
+      unsigned int m = 0u;
+      if (active) {
+#pragma unroll
+        for (int j = 1; j < DRC_MAX_R; ++j) {
+#pragma unroll
+          for (int i = 0; i < j; ++i) {
+            if (j < r) {
+              bool ne = (v[i].x != v[j].x) | (v[i].y != v[j].y) | (v[i].z != v[j].z) | (v[i].w != v[j].w);
+              m |= ne ? (1u << pair_bit(i, j)) : 0u;
+            }
+          }
+        }
+      }
+      // warp OR, then one shared atomic per warp (mismatches are rare)
+      m = __reduce_or_sync(0xffffffffu, m);
+      if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_mask[g], m);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.G && s_mask[threadIdx.x])
+      atomicOr(&a.neq_mask[threadIdx.x * a.tv.ntensors + tensor], s_mask[threadIdx.x]);
+    __syncthreads();
+  }
+}
+
+struct ResolveArgs {
+  const unsigned int* neq_mask;   // [G][T]
+  const int* group_table;         // [G][max_r]
+  int G, max_r, T;
+  int* winner_slot;               // [G][T] winning worker slot
+  int* winner_member;             // [G][T] winning member index (diagnostics), may be null
+  unsigned int* clear_mask;       // same buffer as neq_mask: cleared for the next step after use
+};
+
+__global__ void vote_resolve_kernel(const __grid_constant__ ResolveArgs a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.G * a.T) return;
+  int g = i / a.T;
+  unsigned int mask = a.neq_mask[i];
+  int cand = 0, count = 0;
+  for (int k = 0; k < a.max_r; ++k) {
+    if (a.group_table[g * a.max_r + k] < 0) break;
+    if (count == 0) { cand = k; count = 1; }
+    else {
+      int lo = cand < k ? cand : k, hi = cand < k ? k : cand;
+      bool equal = !((mask >> pair_bit(lo, hi)) & 1u);
+      count += equal ? 1 : -1;
+    }
+  }
+  a.winner_slot[i] = a.group_table[g * a.max_r + cand];
+  if (a.winner_member) a.winner_member[i] = cand;
+  if (a.clear_mask) a.clear_mask[i] = 0u;
+}
+
+extern "C" int drc_vote_compare(const VoteArgs* args, int grid, cudaStream_t stream) {
+  if (args->max_r > DRC_MAX_R || args->G > DRC_MAX_WORKERS) return (int)cudaErrorInvalidValue;
+  vote_compare_kernel<<<grid, DRC_THREADS, 0, stream>>>(*args);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int drc_vote_resolve(const ResolveArgs* args, cudaStream_t stream) {
+  int n = args->G * args->T;
+  vote_resolve_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*args);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int drc_sizeof_VoteArgs() { return (int)sizeof(VoteArgs); }
+extern "C" int drc_sizeof_ResolveArgs() { return (int)sizeof(ResolveArgs); }
