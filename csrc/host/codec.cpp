@@ -12,7 +12,10 @@
 //   plane   := u8 mode  payload
 //       mode 0 RAW    payload = n bytes
 //       mode 1 CONST  payload = 1 byte                      (all bytes of the plane equal)
-//       mode 2 PACK   payload = u8 base, u8 bits, ceil(n*bits/8) bytes   (byte - base  <  2^bits, bits in {1,2,4})
+//       mode 2 PACK   payload = u8 base, u8 bits, ceil(n*bits/8) bytes   (byte - base  <  2^bits, bits in 1..7)
+//
+// itemsize bit 8 (0x100) = "float32 words": each 32-bit word is rotated left by one before the byte split so that
+// the sign bit leaves the exponent byte (the exponent plane of a gradient tensor then spans a few values only).
 #include <stdint.h>
 #include <string.h>
 
@@ -31,15 +34,16 @@ void encode_plane(Writer& w, const uint8_t* plane, uint32_t n) {
   for (uint32_t i = 0; i < n; ++i) { if (plane[i] < lo) lo = plane[i]; if (plane[i] > hi) hi = plane[i]; }
   const uint32_t range = (uint32_t)hi - lo;
   if (range == 0) { w.put8(1); w.put8(lo); return; }
-  int bits = range < 2 ? 1 : range < 4 ? 2 : range < 16 ? 4 : 0;
-  if (!bits) { w.put8(0); w.put(plane, n); return; }
+  int bits = 0;
+  while ((1u << bits) <= range) ++bits;            // smallest width with range < 2^bits
+  if (bits >= 8) { w.put8(0); w.put(plane, n); return; }
   w.put8(2); w.put8(lo); w.put8((uint8_t)bits);
-  const uint32_t per = 8 / bits;
-  for (uint32_t i = 0; i < n; i += per) {
-    uint8_t b = 0;
-    for (uint32_t j = 0; j < per && i + j < n; ++j) b |= (uint8_t)((plane[i + j] - lo) << (j * bits));
-    w.put8(b);
+  uint32_t acc = 0; int fill = 0;                  // little-endian bitstream
+  for (uint32_t i = 0; i < n; ++i) {
+    acc |= (uint32_t)(plane[i] - lo) << fill; fill += bits;
+    while (fill >= 8) { w.put8((uint8_t)(acc & 0xff)); acc >>= 8; fill -= 8; }
   }
+  if (fill > 0) w.put8((uint8_t)(acc & 0xff));
 }
 }  // namespace
 
@@ -47,24 +51,35 @@ extern "C" {
 
 // Worst-case size of the encoded stream for `raw_bytes` of payload.
 uint64_t drc_codec_bound(uint64_t raw_bytes, uint32_t itemsize) {
+  itemsize &= 0xff;
   uint64_t elems = raw_bytes / (itemsize ? itemsize : 1) + 1;
   uint64_t blocks = elems / BLOCK_ELEMS + 1;
   return 20 + raw_bytes + blocks * itemsize * 3 + 16;
 }
 
 // Returns encoded size, or 0 on failure (dst too small / bad arguments).
-uint64_t drc_codec_encode(const uint8_t* src, uint64_t raw_bytes, uint32_t itemsize, uint8_t* dst, uint64_t dst_cap) {
-  if (itemsize == 0 || itemsize > 16 || raw_bytes % itemsize) return 0;
+uint64_t drc_codec_encode(const uint8_t* src, uint64_t raw_bytes, uint32_t itemsize_flags, uint8_t* dst, uint64_t dst_cap) {
+  const uint32_t itemsize = itemsize_flags & 0xff;
+  const bool rot = (itemsize_flags & 0x100) != 0;
+  if (itemsize == 0 || itemsize > 16 || raw_bytes % itemsize || (rot && itemsize != 4)) return 0;
   Writer w{dst, dst + dst_cap, true};
   uint32_t be = BLOCK_ELEMS;
-  w.put(&MAGIC, 4); w.put(&itemsize, 4); w.put(&raw_bytes, 8); w.put(&be, 4);
+  w.put(&MAGIC, 4); w.put(&itemsize_flags, 4); w.put(&raw_bytes, 8); w.put(&be, 4);
   const uint64_t elems = raw_bytes / itemsize;
   uint8_t plane[BLOCK_ELEMS];
   for (uint64_t e0 = 0; e0 < elems; e0 += BLOCK_ELEMS) {
     const uint32_t n = (uint32_t)((elems - e0) < BLOCK_ELEMS ? (elems - e0) : BLOCK_ELEMS);
     for (uint32_t p = 0; p < itemsize; ++p) {
       const uint8_t* s = src + e0 * itemsize + p;
-      for (uint32_t i = 0; i < n; ++i) plane[i] = s[(uint64_t)i * itemsize];
+      if (!rot) {
+        for (uint32_t i = 0; i < n; ++i) plane[i] = s[(uint64_t)i * itemsize];
+      } else {
+        for (uint32_t i = 0; i < n; ++i) {
+          uint32_t v; memcpy(&v, src + (e0 + i) * 4, 4);
+          v = (v << 1) | (v >> 31);
+          plane[i] = (uint8_t)(v >> (8 * p));
+        }
+      }
       encode_plane(w, plane, n);
     }
   }
@@ -83,9 +98,12 @@ uint64_t drc_codec_raw_size(const uint8_t* src, uint64_t n) {
 // Returns decoded size, or 0 on failure.
 uint64_t drc_codec_decode(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dst_cap) {
   if (n < 20) return 0;
-  uint32_t magic, itemsize, be; uint64_t raw;
-  memcpy(&magic, src, 4); memcpy(&itemsize, src + 4, 4); memcpy(&raw, src + 8, 8); memcpy(&be, src + 16, 4);
-  if (magic != MAGIC || itemsize == 0 || itemsize > 16 || be != BLOCK_ELEMS || raw > dst_cap || raw % itemsize) return 0;
+  uint32_t magic, itemsize_flags, be; uint64_t raw;
+  memcpy(&magic, src, 4); memcpy(&itemsize_flags, src + 4, 4); memcpy(&raw, src + 8, 8); memcpy(&be, src + 16, 4);
+  const uint32_t itemsize = itemsize_flags & 0xff;
+  const bool rot = (itemsize_flags & 0x100) != 0;
+  if (magic != MAGIC || itemsize == 0 || itemsize > 16 || be != BLOCK_ELEMS || raw > dst_cap || raw % itemsize ||
+      (rot && itemsize != 4)) return 0;
   const uint8_t* p = src + 20; const uint8_t* end = src + n;
   const uint64_t elems = raw / itemsize;
   uint8_t plane[BLOCK_ELEMS];
@@ -99,14 +117,25 @@ uint64_t drc_codec_decode(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t
       else if (mode == 2) {
         if (p + 2 > end) return 0;
         const uint8_t base = *p++; const uint32_t bits = *p++;
-        if (bits != 1 && bits != 2 && bits != 4) return 0;
-        const uint32_t per = 8 / bits, nb = (cnt + per - 1) / per, mask = (1u << bits) - 1;
+        if (bits < 1 || bits > 7) return 0;
+        const uint32_t nb = (cnt * bits + 7) / 8, mask = (1u << bits) - 1;
         if (p + nb > end) return 0;
-        for (uint32_t i = 0; i < cnt; ++i) plane[i] = (uint8_t)(base + ((p[i / per] >> ((i % per) * bits)) & mask));
+        for (uint32_t i = 0; i < cnt; ++i) {
+          const uint32_t bit = i * bits, byte = bit >> 3, sh = bit & 7;
+          uint32_t word = p[byte] | (byte + 1 < nb ? (uint32_t)p[byte + 1] << 8 : 0u);
+          plane[i] = (uint8_t)(base + ((word >> sh) & mask));
+        }
         p += nb;
       } else return 0;
       uint8_t* d = dst + e0 * itemsize + pl;
       for (uint32_t i = 0; i < cnt; ++i) d[(uint64_t)i * itemsize] = plane[i];
+    }
+    if (rot) {
+      for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t v; memcpy(&v, dst + (e0 + i) * 4, 4);
+        v = (v >> 1) | (v << 31);
+        memcpy(dst + (e0 + i) * 4, &v, 4);
+      }
     }
   }
   return raw;

@@ -1,0 +1,101 @@
+"""Linear layer backed by the hand-written tcgen05 GEMM (``csrc/cuda/gemm_tcgen05.cu``).
+
+All three products of a linear layer run on the same kernel without transpose copies, by describing operands to TMA
+/ UMMA as K-major or MN-major:
+
+    y  = x  W^T   A = x  (K-major)   B = W  (K-major)     + fused bias (+ReLU) epilogue
+    dx = dy W     A = dy (K-major)   B = W  (MN-major)
+    dW = dy^T x   A = dy (MN-major)  B = x  (MN-major)
+
+Shapes whose rows are not 16-byte multiples (e.g. 10-wide logits as an MN-major operand) and non-bf16 / CPU tensors
+take the cuBLAS / ATen path -- that is a per-call shape gate, not a silent global fallback: ``backend_counters`` records
+which path served every call so tests and the bench can assert the tensor-core path ran.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+backend_counters = {"tcgen05": 0, "aten": 0}
+
+
+def _use_native(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16 and os.environ.get("DRACO_LINEAR", "tcgen05") == "tcgen05"
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import kernels as K
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        if K.gemm_supported(x2, weight) and weight.is_contiguous():
+            backend_counters["tcgen05"] += 1
+            y = K.gemm_bf16(x2, weight, bias=bias)
+        else:
+            backend_counters["aten"] += 1
+            y = F.linear(x2, weight, bias)
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import kernels as K
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if K.gemm_supported(dy2, weight) and weight.shape[1] >= 64:
+                backend_counters["tcgen05"] += 1
+                dx = K.gemm_bf16(dy2, weight, b_mn=True)
+            else:
+                backend_counters["aten"] += 1
+                dx = dy2 @ weight
+            dx = dx.reshape(x.shape)
+        if ctx.needs_input_grad[1]:
+            if K.gemm_supported(dy2, x2) and x2.shape[1] >= 64:
+                backend_counters["tcgen05"] += 1
+                dw = K.gemm_bf16(dy2, x2, a_mn=True, b_mn=True)
+            else:
+                backend_counters["aten"] += 1
+                dw = dy2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db
+
+
+class Linear(nn.Module):
+    """Drop-in ``nn.Linear`` (same parameter names / init) whose CUDA bf16 path is the tcgen05 GEMM."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True) -> None:
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1.0 / math.sqrt(self.in_features) if self.in_features > 0 else 0.0
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if _use_native(x) and self.weight.dtype == torch.bfloat16:
+            return _LinearFn.apply(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
+
+    def extra_repr(self) -> str:
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"

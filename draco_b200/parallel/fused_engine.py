@@ -1,0 +1,264 @@
+"""The product transport (``--transport nvl``): every byte of a training step moves through sm_100a kernels.
+
+Step anatomy (one PS + P logical workers hosted by ``nprocs`` GPU processes; see placement.py):
+
+    worker GPU                                                   PS GPU
+    ----------                                                   ------
+    wait_flags(params_ready >= t)        [spin on local flag]
+    cast_params fp32 -> bf16
+    forward / backward  (x R sub-batches under the cyclic code)
+    push_encode: encode + adversary + 16 B peer stores  ------>  grad_in[w]   + release flag grad_ready[w] = t
+                                                                 wait_flags(grad_ready[*] >= t)
+                                                                 vote | project+locate | krum | geomedian   (decode)
+    params arena  <------ multimem.st / peer stores  ----------  aggregate_update: SGD-momentum + broadcast
+    flag params_ready = t+1  <---------------------------------  (last CTA)
+
+There is no NCCL / MPI call and no host synchronisation anywhere in that loop; ordering between GPUs is carried by
+step-stamped, monotonically increasing flag words (acquire/release at system scope).  The whole per-process sequence is
+captured once in a CUDA graph and replayed; the step number lives in device memory so replays advance it.
+
+Reference counterparts: master loops src/master/{baseline,rep,cyclic}_master.py ``start()``; worker loops
+src/worker/*_worker.py ``train()``; all mpi4py traffic listed in SURVEY.md section 2.3 "Collective / message call sites".
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..codes.adversary import attack_code, generate_schedule
+from ..config import JobConfig
+from ..data import BatchPlan, TensorDataset
+from ..ops import kernels as K
+from .arena import ArenaLayout
+from .placement import Placement
+from .ps import FusedPS, build_codes
+from .symm import SymmContext
+from .worker import WorkerCompute, make_model
+
+FLAG_STRIDE = 128            # bytes between flag words (one per 128-B line)
+FLAG_BYTES = 8192
+
+
+class FusedEngine:
+    def __init__(self, cfg: JobConfig, rank: int, nprocs: int, device: torch.device, dataset: Optional[TensorDataset],
+                 group=None):
+        assert device.type == "cuda", "the nvl transport needs a GPU"
+        self.cfg, self.rank, self.nprocs, self.device, self.group = cfg, rank, nprocs, device, group
+        self.place = Placement(cfg.num_workers, nprocs)
+        self.P = cfg.num_workers
+        self.is_ps = rank == 0
+        self.local_workers = self.place.local_workers(rank)
+        self.active = self.is_ps or bool(self.local_workers)
+        self.groups, self.code = build_codes(cfg)
+        self.cyclic = cfg.approach == "cyclic"
+        self.esize = 8 if self.cyclic else 4
+        self.step = 1                                   # host mirror of the device step counter
+        self.kernels_per_step = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._use_graph = cfg.cuda_graphs and cfg.err_mode != "omniscient"
+
+        if cfg.deterministic:
+            torch.backends.cudnn.deterministic = True
+            torch.backends.cudnn.benchmark = False
+            os.environ.setdefault("CUBLAS_WORKSPACE_CONFIG", ":4096:8")
+
+        model = make_model(cfg)
+        bf16 = cfg.dtype == "bf16"
+        self.layout = ArenaLayout.from_model(model, bf16, channels_last=True)
+        D = self.layout.total
+
+        # ---------------- symmetric regions -------------------------------------------------------------
+        self.symm = SymmContext(device, rank, nprocs, group)
+        gran = None
+        want_mc = cfg.multicast != "off" and nprocs > 1
+        regA = self.symm.alloc("params", D * 4 + FLAG_BYTES, gran)
+        self.params_f32 = regA.tensor[: D * 4].view(torch.float32)
+        self.flagsA = regA.tensor[D * 4: D * 4 + FLAG_BYTES].view(torch.int64)
+        self.params_ready_ptr = regA.ptr + D * 4
+        if self.is_ps:
+            regB = self.symm.alloc("grad_in", self.P * D * self.esize + FLAG_BYTES)
+            self.grad_in = regB.tensor[: self.P * D * self.esize].view(torch.float32)
+            self.flagsB = regB.tensor[self.P * D * self.esize: self.P * D * self.esize + FLAG_BYTES].view(torch.int64)
+        all_procs = list(range(nprocs))
+        mapA = self.symm.share("params", exporters=all_procs, importers=[0])
+        mapB = self.symm.share("grad_in", exporters=[0], importers=all_procs)
+        self.ps_grad_base = mapB[0].ptr
+        self.ps_flag_base = mapB[0].ptr + self.P * D * self.esize
+        self.mc_params = None
+        if want_mc:
+            self.mc_params = self.symm.bind_multicast("params")
+            if self.mc_params is None and cfg.multicast == "on":
+                raise RuntimeError("--multicast on, but NVLS multicast could not be set up")
+
+        # ---------------- device-side control words -----------------------------------------------------
+        self.step_dev = torch.ones(1, dtype=torch.int64, device=device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        self.counters = torch.zeros(16, dtype=torch.int32, device=device)
+        sched = generate_schedule(self.P, cfg.worker_fail, cfg.max_steps)
+        self.schedule = sched
+        use_adv = cfg.err_mode != "none" and cfg.worker_fail > 0
+        self.adv_bitmap = torch.from_numpy(sched.bitmaps().view(np.int32).copy()).to(device) if use_adv else None
+        self.attack = attack_code(cfg.err_mode) if self.adv_bitmap is not None else 0
+
+        # ---------------- roles -------------------------------------------------------------------------
+        self.worker: Optional[WorkerCompute] = None
+        self.ps: Optional[FusedPS] = None
+        if self.local_workers or self.is_ps:
+            plan = make_plan(cfg, dataset, self.groups)
+            # the PS process also builds the model: its initial parameters are the job's initial parameters
+            self.worker = WorkerCompute(cfg, device, self.local_workers, plan, dataset, self.layout, self.params_f32, model)
+        if self.is_ps:
+            self.ps = FusedPS(cfg, self.layout, device, self.params_f32, self.grad_in, self.groups, self.code)
+            self.dst_ptrs = [mapA[p].ptr for p in self.place.worker_procs() if p != 0]
+            self.param_flag_ptrs = [mapA[p].ptr + D * 4 for p in self.place.active_procs()]
+        self._initial_broadcast()
+
+    # ------------------------------------------------------------------ setup helpers
+    def _initial_broadcast(self) -> None:
+        """PS -> every process: initial parameters, then params_ready = 1 (reference: first Bcast of the loop)."""
+        if self.is_ps:
+            nbytes = self.layout.total * 4
+            lib = K.N.cuda()
+            st = torch.cuda.current_stream().cuda_stream
+            for d in self.dst_ptrs:
+                K.N.check(lib.drc_rt_memcpy_async(d, self.params_f32.data_ptr(), nbytes, st), "initial broadcast")
+            torch.cuda.synchronize()
+        self._barrier()
+        if self.is_ps:
+            K.set_flags(self.param_flag_ptrs, self.step_dev, 0)
+            torch.cuda.synchronize()
+        self._barrier()
+
+    def _barrier(self) -> None:
+        if self.nprocs > 1:
+            dist.barrier(group=self.group)
+
+    def slot_ptr(self, w: int) -> int:
+        return self.ps_grad_base + (w - 1) * self.layout.total * self.esize
+
+    def grad_flag_ptr(self, w: int) -> int:
+        return self.ps_flag_base + (w - 1) * FLAG_STRIDE
+
+    # ------------------------------------------------------------------ the step
+    def _enqueue_local_step(self, step_host: Optional[int]) -> int:
+        """Enqueue everything this process contributes to one step.  Returns #kernels of ours launched."""
+        cfg, L = self.cfg, self.layout
+        n = 0
+        if self.local_workers:
+            wc = self.worker
+            K.wait_flags([self.params_ready_ptr], self.step_dev, 0, self.error, cfg.spin_timeout_s); n += 1
+            if wc.bf16:
+                K.cast_params(L, wc.binder.params_f32, wc.binder.params_c); n += 1
+            for w in self.local_workers:
+                wc.forward_backward(w, step_host)
+                g32 = [g[0] for g in wc.grads]
+                g16 = [g[1] for g in wc.grads]
+                coef = list(self.code.coeffs_of(w - 1)) if self.cyclic else None
+                lying_now = (step_host is not None and cfg.err_mode == "omniscient"
+                             and self.schedule.is_adversary(w, step_host))
+                if lying_now:
+                    honest = 0
+                    for h in range(1, self.P + 1):
+                        if not self.schedule.is_adversary(h, step_host):
+                            honest |= 1 << (h - 1)
+                    flags = [self.grad_flag_ptr(h) for h in range(1, self.P + 1) if (honest >> (h - 1)) & 1]
+                    K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s)
+                    K.omniscient(self.ps_grad_base, L.total, honest, w - 1, cfg.attack_magnitude, L.total,
+                                 step_ptr=self.step_dev, done_counter=self.counters[1:2], flag=self.grad_flag_ptr(w))
+                    n += 2
+                else:
+                    K.push_encode(L, g32, g16, self.slot_ptr(w), step_ptr=self.step_dev, worker=w - 1,
+                                  done_counter=self.counters[1:2], flag=self.grad_flag_ptr(w), coef=coef,
+                                  adv_bitmap=self.adv_bitmap, adv_len=len(self.schedule.ranks),
+                                  attack=self.attack if self.attack != 4 else 0, magnitude=cfg.attack_magnitude,
+                                  seed=cfg.seed)
+                    n += 1
+        if self.is_ps:
+            flags = [self.flagsB.data_ptr() + i * FLAG_STRIDE for i in range(self.P)]
+            K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s); n += 1
+            n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
+                                      dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
+        K.step_add(self.step_dev, 1); n += 1
+        return n
+
+    def _capture(self) -> None:
+        # honour the "omniscient needs the host step" restriction
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            # warm-up outside capture: lazy cuDNN/cuBLAS init must not happen while capturing.  The warm-up runs the
+            # real step 1 and 2 (they count as training steps).
+            for _ in range(2):
+                self._stage(self.step)
+                self.kernels_per_step = self._enqueue_local_step(self.step)
+                self.step += 1
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._check_error()
+        self.graph = torch.cuda.CUDAGraph()
+        self._stage(self.step)
+        with torch.cuda.graph(self.graph):
+            self.kernels_per_step = self._enqueue_local_step(None)
+        # capture does not execute: nothing to account for
+
+    def _stage(self, step: int) -> int:
+        if self.local_workers and self.worker.dataset is not None:
+            return self.worker.stage_batches(step)
+        return 0
+
+    def train_step(self, stage: bool = True) -> None:
+        """Enqueue one full step for this process (asynchronous; call ``read_metrics``/``synchronize`` to wait)."""
+        if not self.active:
+            self.step += 1
+            return
+        if self._use_graph:
+            if self.graph is None:
+                self._capture()
+            if stage:
+                self._stage(self.step)
+            self.graph.replay()
+        else:
+            if stage:
+                self._stage(self.step)
+            self.kernels_per_step = self._enqueue_local_step(self.step)
+        self.step += 1
+
+    # ------------------------------------------------------------------ host-visible results
+    def _check_error(self) -> None:
+        e = int(self.error.item())
+        if e:
+            raise RuntimeError(f"rank {self.rank}: spin-wait watchdog fired (flag index {e - 1}) -- a peer never arrived")
+
+    def read_metrics(self) -> Dict[str, float]:
+        """Device -> host read of the step's loss / Prec@1 / Prec@5 (mean over local workers).  Synchronises."""
+        if not self.local_workers:
+            torch.cuda.current_stream().synchronize()
+            self._check_error()
+            return {}
+        m = torch.stack([self.worker.metrics[w] for w in self.local_workers]).mean(0)
+        vals = m.tolist()
+        self._check_error()
+        return {"loss": vals[0], "prec1": vals[1], "prec5": vals[2]}
+
+    def synchronize(self) -> None:
+        torch.cuda.synchronize()
+        self._check_error()
+
+    def master_params(self) -> torch.Tensor:
+        """The fp32 parameter arena of this process (the PS's is the master copy)."""
+        return self.params_f32
+
+    def close(self) -> None:
+        self.symm.close()
+
+
+def make_plan(cfg: JobConfig, dataset: Optional[TensorDataset], groups) -> BatchPlan:
+    n = len(dataset) if dataset is not None else cfg.synthetic_size
+    return BatchPlan(cfg.approach, n, cfg.batch_size, cfg.num_workers,
+                     group_of=groups.rank_to_group if groups is not None else None,
+                     group_seeds=groups.seeds if groups is not None else None,
+                     seed=428, redundancy=cfg.redundancy if cfg.approach == "cyclic" else 1)

@@ -1,0 +1,210 @@
+"""Worker-side compute: batches in, gradients left in the flat gradient arenas.
+
+Reference counterparts: ``DistributedWorker`` / ``CodedWorker`` / ``CyclicWorker`` (src/worker/baseline_worker.py:67-158,
+rep_worker.py:63-155, cyclic_worker.py:63-163).  What is kept: one forward/backward per assigned sub-batch (1, or 2s+1
+under the cyclic code), Prec@1/Prec@5/loss per step, local BatchNorm statistics, identical batches (and dropout /
+augmentation randomness) for every holder of a batch.  What moved out: everything about communication -- encode,
+adversary, compression and sends are the transport's business (parallel/fused_engine.py, collective_engine.py), not the
+model's or the worker's.
+
+One ``WorkerCompute`` serves *all* logical workers hosted by a process: they receive the same parameters, so they
+share the model, its parameter arena and the gradient arenas, and differ only in the batches they are fed.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ..config import JobConfig
+from ..data import BatchPlan, TensorDataset, augment_cifar
+from ..models import build_model
+from .arena import ArenaLayout, ModelBinder
+
+
+def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1, 5)) -> List[torch.Tensor]:
+    """Prec@k in percent (the reference carries four copies of this helper, e.g. src/worker/utils.py:22-35)."""
+    maxk = min(max(topk), output.shape[1])
+    _, pred = output.float().topk(maxk, 1, True, True)
+    correct = pred.t().eq(target.view(1, -1))
+    return [correct[:min(k, maxk)].reshape(-1).float().sum() * (100.0 / target.shape[0]) for k in topk]
+
+
+def make_model(cfg: JobConfig) -> torch.nn.Module:
+    torch.manual_seed(cfg.seed)
+    kwargs = {}
+    if cfg.num_classes != 10 and (cfg.network.startswith("ResNet") or cfg.network.startswith("VGG")):
+        kwargs["num_classes"] = cfg.num_classes
+    return build_model(cfg.network, **kwargs)
+
+
+class WorkerCompute:
+    def __init__(self, cfg: JobConfig, device: torch.device, local_workers: List[int], plan: BatchPlan,
+                 dataset: Optional[TensorDataset], layout: Optional[ArenaLayout] = None,
+                 params_f32: Optional[torch.Tensor] = None, model: Optional[torch.nn.Module] = None):
+        self.cfg, self.device, self.local_workers, self.plan, self.dataset = cfg, torch.device(device), local_workers, plan, dataset
+        self.bf16 = cfg.dtype == "bf16" and self.device.type == "cuda"
+        self.model = model if model is not None else make_model(cfg)
+        self.channels_last = self.device.type == "cuda"
+        self.layout = layout or ArenaLayout.from_model(self.model, self.bf16, self.channels_last)
+        self.binder = ModelBinder(self.model, self.layout, self.device, self.bf16, params_f32)
+        self.R = cfg.redundancy if cfg.approach == "cyclic" else 1
+        self.grads: List[Tuple[torch.Tensor, Optional[torch.Tensor]]] = [self.binder.new_grad_arenas() for _ in range(self.R)]
+        self.model.train()
+        self.has_dropout = any(isinstance(m, torch.nn.Dropout) for m in self.model.modules())
+        c, h, w = self.model.input_shape if hasattr(self.model, "input_shape") else (3, 32, 32)
+        if dataset is not None:
+            c, h, w = dataset.images.shape[1:]
+        B = cfg.batch_size
+        self.x_u8: Dict[int, List[torch.Tensor]] = {}
+        self.y: Dict[int, List[torch.Tensor]] = {}
+        self.metrics: Dict[int, torch.Tensor] = {}
+        for wk in local_workers:
+            self.x_u8[wk] = [torch.zeros(B, c, h, w, dtype=torch.uint8, device=self.device) for _ in range(self.R)]
+            self.y[wk] = [torch.zeros(B, dtype=torch.long, device=self.device) for _ in range(self.R)]
+            self.metrics[wk] = torch.zeros(3, dtype=torch.float32, device=self.device)   # loss, prec1, prec5
+        self._pinned = None
+        self._pin_slot = 0
+        self._pin_events = [None, None]
+        self._dataset_dev = None
+        if dataset is not None:
+            self._mean = dataset.mean.to(self.device)
+            self._std = dataset.std.to(self.device)
+        else:
+            self._mean = torch.zeros(1, c, 1, 1, device=self.device)
+            self._std = torch.ones(1, c, 1, 1, device=self.device)
+        self.h2d_bytes = 0
+
+    # ------------------------------------------------------------------ input staging
+    def _ensure_pinned(self):
+        if self._pinned is None:
+            n = len(self.local_workers) * self.R
+            shape = self.x_u8[self.local_workers[0]][0].shape
+            pin = self.device.type == "cuda"
+            self._pinned = [(torch.zeros((n,) + tuple(shape), dtype=torch.uint8, pin_memory=pin),
+                             torch.zeros((n, shape[0]), dtype=torch.long, pin_memory=pin)) for _ in range(2)]
+
+    def stage_batches(self, step: int) -> int:
+        """Host -> device copy of every sub-batch this process needs at ``step``.  Returns bytes copied."""
+        assert self.dataset is not None
+        if self.cfg.data_on_device and self.device.type == "cuda":
+            return self._stage_from_device(step)
+        self._ensure_pinned()
+        slot = self._pin_slot
+        self._pin_slot ^= 1
+        if self._pin_events[slot] is not None:
+            self._pin_events[slot].synchronize()
+        px, py = self._pinned[slot]
+        i = 0
+        for wk in self.local_workers:
+            ids = self.plan.batch_ids(step, wk)
+            for k, idx in enumerate(self.plan.indices(step, wk)):
+                tidx = torch.from_numpy(np.ascontiguousarray(idx)).long()
+                if self.cfg.augment and self.dataset.name == "Cifar10":
+                    px[i].copy_(augment_cifar(self.dataset.images[tidx], self.cfg.seed * 7919 + step * 131 + ids[k]))
+                else:
+                    torch.index_select(self.dataset.images, 0, tidx, out=px[i])
+                torch.index_select(self.dataset.labels, 0, tidx, out=py[i])
+                i += 1
+        nbytes = 0
+        i = 0
+        for wk in self.local_workers:
+            for k in range(self.R):
+                self.x_u8[wk][k].copy_(px[i], non_blocking=True)
+                self.y[wk][k].copy_(py[i], non_blocking=True)
+                nbytes += px[i].numel() + py[i].numel() * 8
+                i += 1
+        if self.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pin_events[slot] = ev
+        self.h2d_bytes = nbytes
+        return nbytes
+
+    def _stage_from_device(self, step: int) -> int:
+        if self._dataset_dev is None:
+            self._dataset_dev = (self.dataset.images.to(self.device), self.dataset.labels.to(self.device))
+        imgs, labels = self._dataset_dev
+        nbytes = 0
+        for wk in self.local_workers:
+            for k, idx in enumerate(self.plan.indices(step, wk)):
+                tidx = torch.from_numpy(np.ascontiguousarray(idx)).long().to(self.device, non_blocking=True)
+                torch.index_select(imgs, 0, tidx, out=self.x_u8[wk][k])
+                torch.index_select(labels, 0, tidx, out=self.y[wk][k])
+                nbytes += tidx.numel() * 8
+        self.h2d_bytes = nbytes
+        return nbytes
+
+    def load_batch(self, wk: int, k: int, x_u8: torch.Tensor, y: torch.Tensor) -> None:
+        """Directly provide a batch (public-API path used by tests / custom loops)."""
+        self.x_u8[wk][k].copy_(x_u8, non_blocking=True)
+        self.y[wk][k].copy_(y, non_blocking=True)
+
+    # ------------------------------------------------------------------ compute
+    def _prep_input(self, x_u8: torch.Tensor) -> torch.Tensor:
+        x = (x_u8.float().div_(255.0).sub_(self._mean)).div_(self._std)
+        if self.bf16:
+            x = x.to(torch.bfloat16)
+        if self.channels_last and x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        return x
+
+    def forward_backward(self, wk: int, step_host: Optional[int] = None) -> None:
+        """Run fwd/bwd for all sub-batches of logical worker ``wk``; gradients land in ``self.grads[k]``.
+        Everything enqueued here is capturable in a CUDA graph (no host sync)."""
+        met = self.metrics[wk]
+        met.zero_()
+        ids = self.plan.batch_ids(step_host or 1, wk) if self.has_dropout else None
+        for k in range(self.R):
+            g32, g16 = self.grads[k]
+            g32.zero_()
+            if g16 is not None:
+                g16.zero_()
+            self.binder.bind_grads(g32, g16)
+            if self.has_dropout and step_host is not None:
+                # identical dropout masks for every holder of this (step, batch)
+                torch.manual_seed((self.cfg.seed * 1000003 + step_host * 8191 + ids[k]) & 0x7FFFFFFF)
+            x = self._prep_input(self.x_u8[wk][k])
+            y = self.y[wk][k]
+            out = self.model(x)
+            loss = F.cross_entropy(out.float(), y)
+            if hasattr(self.model, "backward_single"):
+                self.model.backward_single(loss)
+            else:
+                loss.backward()
+            with torch.no_grad():
+                p1, p5 = accuracy(out.detach(), y)
+                met += torch.stack([loss.detach(), p1, p5]) / self.R
+
+    def flat_gradient(self, k: int = 0) -> torch.Tensor:
+        """fp32 flat gradient of sub-batch k (collective transports; the fused push reads the arenas directly)."""
+        g32, g16 = self.grads[k]
+        return self.binder.flat_grad_f32(g32, g16)
+
+    # ------------------------------------------------------------------ evaluation
+    @torch.no_grad()
+    def evaluate(self, dataset: TensorDataset, batch_size: int = 100, max_batches: Optional[int] = None) -> Dict[str, float]:
+        """Test loss / Prec@1 / Prec@5 (reference: baseline_worker.py:275-293)."""
+        was_training = self.model.training
+        self.model.eval()
+        tot, n = torch.zeros(3, device=self.device), 0
+        mean, std = dataset.mean.to(self.device), dataset.std.to(self.device)
+        for b, s in enumerate(range(0, len(dataset), batch_size)):
+            if max_batches is not None and b >= max_batches:
+                break
+            xb = dataset.images[s:s + batch_size].to(self.device)
+            yb = dataset.labels[s:s + batch_size].to(self.device)
+            x = (xb.float() / 255.0 - mean) / std
+            if self.bf16:
+                x = x.to(torch.bfloat16)
+            if self.channels_last:
+                x = x.contiguous(memory_format=torch.channels_last)
+            out = self.model(x)
+            p1, p5 = accuracy(out, yb)
+            tot += torch.stack([F.cross_entropy(out.float(), yb), p1, p5]) * xb.shape[0]
+            n += xb.shape[0]
+        self.model.train(was_training)
+        tot = (tot / max(n, 1)).tolist()
+        return {"loss": tot[0], "prec1": tot[1], "prec5": tot[2]}

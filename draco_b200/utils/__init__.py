@@ -1,0 +1,1 @@
+"""Codec, checkpoint and metrics utilities."""
