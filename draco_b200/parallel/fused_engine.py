@@ -153,7 +153,11 @@ class FusedEngine:
             K.wait_flags([self.params_ready_ptr], self.step_dev, 0, self.error, cfg.spin_timeout_s); n += 1
             if wc.bf16:
                 K.cast_params(L, wc.binder.params_f32, wc.binder.params_c); n += 1
-            for w in self.local_workers:
+            order = list(self.local_workers)
+            if step_host is not None and cfg.err_mode == "omniscient":
+                # liars read the honest slots: on a shared stream the honest workers must be enqueued first
+                order.sort(key=lambda r: self.schedule.is_adversary(r, step_host))
+            for w in order:
                 wc.forward_backward(w, step_host)
                 g32 = [g[0] for g in wc.grads]
                 g16 = [g[1] for g in wc.grads]

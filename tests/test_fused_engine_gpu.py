@@ -1,0 +1,118 @@
+"""End-to-end tests of the fused (nvl) engine on one GPU (all logical ranks packed on cuda:0) and, when several GPUs are
+visible, across processes over peer memory."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from draco_b200 import JobConfig
+from draco_b200.parallel.trainer import Trainer
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(**kw):
+    base = dict(network="LeNet", dataset="MNIST", batch_size=16, max_steps=12, num_workers=7, transport="nvl", lr=0.02,
+                momentum=0.9, synthetic_size=512, eval_freq=10 ** 6, compress_grad="None", dtype="fp32", cuda_graphs=False)
+    base.update(kw)
+    return JobConfig(**base)
+
+
+def _run(cfg, steps, device=None):
+    dev = device or torch.device("cuda", 0)
+    t = Trainer(cfg, rank=0, world=1, device=dev, quiet=True)
+    losses = [t.train_step()["loss"] for _ in range(steps)]
+    t.synchronize()
+    return t, losses
+
+
+def test_fused_vote_tolerates_adversaries_bitwise():
+    clean, l0 = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=7, worker_fail=0, err_mode="none"), 5)
+    dirty, l1 = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=7, worker_fail=3, err_mode="rev_grad"), 5)
+    assert torch.equal(clean.engine.master_params(), dirty.engine.master_params())
+    assert l0 == l1
+    mean, _ = _run(_cfg(approach="maj_vote", mode="normal", group_size=7, worker_fail=3, err_mode="rev_grad"), 5)
+    assert not torch.allclose(clean.engine.master_params(), mean.engine.master_params(), atol=1e-3)
+
+
+def test_fused_matches_library_op_engine():
+    """Same job through the kernels and through the torch-op PS (nccl transport on one process = no collectives)."""
+    for kw in (dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad"),
+               dict(approach="baseline", mode="normal", worker_fail=0, err_mode="none"),
+               dict(approach="baseline", mode="krum", worker_fail=2, err_mode="constant"),
+               dict(approach="cyclic", worker_fail=2, err_mode="constant")):
+        a, la = _run(_cfg(**kw), 4)
+        b, lb = _run(_cfg(transport="nccl", **kw), 4)
+        pa, pb = a.engine.master_params(), b.engine.master_params()
+        tol = 5e-4 if kw["approach"] == "cyclic" else 2e-5
+        assert torch.allclose(pa, pb, atol=tol), (kw, float((pa - pb).abs().max()))
+
+
+def test_fused_cyclic_and_geomedian_tolerate_adversaries():
+    clean, _ = _run(_cfg(approach="cyclic", worker_fail=2, err_mode="none"), 4)
+    dirty, _ = _run(_cfg(approach="cyclic", worker_fail=2, err_mode="rev_grad"), 4)
+    a, b = clean.engine.master_params(), dirty.engine.master_params()
+    assert torch.allclose(a, b, atol=5e-4), float((a - b).abs().max())
+    assert dirty.engine.ps.flagged.tolist() == [2] * dirty.engine.layout.ntensors
+    gm, lg = _run(_cfg(approach="baseline", mode="geometric_median", worker_fail=2, err_mode="rev_grad", lr=0.05), 10)
+    assert lg[-1] < lg[0] and torch.isfinite(gm.engine.master_params()).all()
+
+
+def test_cuda_graph_replay_equals_eager():
+    kw = dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", network="ResNet18",
+              dataset="Cifar10", batch_size=8, num_workers=3, dtype="bf16", synthetic_size=256)
+    e, le = _run(_cfg(cuda_graphs=False, **kw), 6)
+    g, lg = _run(_cfg(cuda_graphs=True, **kw), 6)
+    assert g.engine.graph is not None
+    assert torch.equal(e.engine.master_params(), g.engine.master_params())
+    assert le == lg
+    assert g.engine.kernels_per_step >= 5
+
+
+def test_replicas_are_bit_identical_resnet_bf16():
+    """Determinism precondition of the majority vote: two replicas of a group produce identical flat gradients."""
+    kw = dict(approach="maj_vote", mode="maj_vote", group_size=2, worker_fail=0, err_mode="none", network="ResNet18",
+              dataset="Cifar10", batch_size=16, num_workers=2, dtype="bf16", synthetic_size=256)
+    t, _ = _run(_cfg(**kw), 2)
+    D = t.engine.layout.total
+    slots = t.engine.grad_in.view(2, D)
+    assert torch.equal(slots[0], slots[1]) and float(slots[0].abs().sum()) > 0
+    assert t.engine.ps.winner_member.abs().sum().item() == 0
+
+
+def test_omniscient_attack_and_vgg_dropout_replicas():
+    om, lo = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=7, worker_fail=2, err_mode="omniscient"), 3)
+    cl, lc = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=7, worker_fail=0, err_mode="none"), 3)
+    assert torch.equal(om.engine.master_params(), cl.engine.master_params())
+    kw = dict(approach="cyclic", worker_fail=1, err_mode="constant", network="VGG11", dataset="Cifar10", batch_size=8,
+              num_workers=3, dtype="bf16", synthetic_size=128, lr=0.01)
+    v, lv = _run(_cfg(**kw), 3)
+    assert v.engine.ps.flagged.tolist() == [1] * v.engine.layout.ntensors      # dropout masks agreed across holders
+    assert all(l == l for l in lv)
+
+
+def test_smoke_entry():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.smoke()
+
+
+@pytest.mark.multigpu
+def test_multi_process_peer_memory_matches_single_process():
+    """2 GPU processes over peer memory (+ NVLS when available) == the same job packed on one GPU."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    script = os.path.join(ROOT, "tests", "mp_equiv.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True,
+                         timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    rec = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    single, _ = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad",
+                          network="ResNet18", dataset="Cifar10", batch_size=8, dtype="bf16", synthetic_size=256,
+                          cuda_graphs=True), 6)
+    assert abs(single.engine.master_params().double().sum().item() - rec["param_sum"]) < 1e-9 * max(1.0, abs(rec["param_sum"]))
+    assert rec["worker_param_sum"] == rec["param_sum"]

@@ -1,0 +1,98 @@
+"""tcgen05 GEMM (csrc/cuda/gemm_tcgen05.cu) and the Linear layer built on it, against fp32 PyTorch references."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from draco_b200.ops import kernels
+    return kernels
+
+
+def _rel_err(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6))
+
+
+SHAPES = [(128, 128, 64), (256, 192, 512), (300, 504, 784), (128, 800, 784), (77, 136, 72), (4096, 512, 4608),
+          (1000, 16, 512), (64, 64, 8), (130, 264, 1032)]
+
+
+@pytest.mark.parametrize("M,N,Kd", SHAPES)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_all_operand_orders(K, M, N, Kd, a_mn, b_mn):
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(M * 7 + N * 3 + Kd)
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operand needs a 16-byte row pitch")
+    A = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
+    B = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    A_in = A.t().contiguous() if a_mn else A
+    B_in = B.t().contiguous() if b_mn else B
+    out = K.gemm_bf16(A_in, B_in, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    assert _rel_err(out, ref) < 2e-3, _rel_err(out, ref)
+    out16 = K.gemm_bf16(A_in, B_in, a_mn=a_mn, b_mn=b_mn)
+    assert _rel_err(out16, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("block_n", [32, 64, 128])
+def test_gemm_block_n_variants_bias_relu_accumulate(K, block_n):
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(block_n)
+    M, N, Kd = 515, 328, 1000
+    A = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
+    B = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    ref = torch.relu(A.float() @ B.float().t() + bias)
+    out = K.gemm_bf16(A, B, out_dtype=torch.float32, bias=bias, relu=True, block_n=block_n)
+    assert _rel_err(out, ref) < 2e-3
+    out_b = K.gemm_bf16(A, B, bias=bias.to(torch.bfloat16), relu=True, block_n=block_n)
+    assert _rel_err(out_b, ref) < 2e-2
+    acc = torch.ones(M, N, device=dev)
+    K.gemm_bf16(A, B, out=acc, accumulate=True, block_n=block_n)
+    assert _rel_err(acc, A.float() @ B.float().t() + 1.0) < 2e-3
+
+
+def test_gemm_odd_ldc_scalar_store_path(K):
+    dev = torch.device("cuda", 0)
+    A = torch.randn(200, 512, device=dev).to(torch.bfloat16)
+    B = torch.randn(10, 512, device=dev).to(torch.bfloat16)       # the CIFAR classifier: N = 10
+    ref = A.float() @ B.float().t()
+    assert _rel_err(K.gemm_bf16(A, B, out_dtype=torch.float32), ref) < 2e-3
+    assert _rel_err(K.gemm_bf16(A, B), ref) < 1.5e-2
+
+
+def test_gemm_is_deterministic(K):
+    dev = torch.device("cuda", 0)
+    A = torch.randn(1024, 2048, device=dev).to(torch.bfloat16)
+    B = torch.randn(768, 2048, device=dev).to(torch.bfloat16)
+    o1 = K.gemm_bf16(A, B)
+    o2 = K.gemm_bf16(A, B)
+    assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("batch,fin,fout", [(128, 512, 512), (128, 784, 800), (128, 512, 10), (96, 800, 500)])
+def test_linear_layer_forward_backward(batch, fin, fout):
+    from draco_b200.ops.linear import Linear, backend_counters
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    lin = Linear(fin, fout).to(dev).to(torch.bfloat16)
+    x = torch.randn(batch, fin, device=dev).to(torch.bfloat16).requires_grad_(True)
+    before = backend_counters["tcgen05"]
+    y = lin(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    assert backend_counters["tcgen05"] > before, "the tensor-core path did not run"
+    w32, b32 = lin.weight.detach().float().requires_grad_(True), lin.bias.detach().float().requires_grad_(True)
+    x32 = x.detach().float().requires_grad_(True)
+    y32 = F.linear(x32, w32, b32)
+    y32.backward(gy.float())
+    assert _rel_err(y, y32) < 1.5e-2
+    assert _rel_err(x.grad, x32.grad) < 2e-2
+    assert _rel_err(lin.weight.grad, w32.grad) < 2e-2
+    assert _rel_err(lin.bias.grad, b32.grad) < 2e-2
