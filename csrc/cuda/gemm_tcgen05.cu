@@ -372,8 +372,10 @@ int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap&
 // Requirements: bf16 operands, 16-byte aligned bases, leading dimensions multiple of 8 elements.
 extern "C" int drc_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C, long long ldc,
                              int c_fp32, int M, int N, int K, const float* bias_f32, const void* bias_bf16, int relu, int accumulate,
-                             int block_n, int num_sms, cudaStream_t stream) {
+                             int block_n, int num_sms, int device, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  // autograd worker threads start without a bound context; the driver-API tensor-map encode needs one
+  if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -3;
   if (block_n == 0) block_n = (N > 64) ? 128 : (N > 32 ? 64 : (b_mn ? 64 : 32));
   if (b_mn && block_n < 64) block_n = 64;

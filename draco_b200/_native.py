@@ -182,7 +182,7 @@ def cuda() -> C.CDLL:
             "drc_pair_dist": [C.POINTER(PairDistArgs), C.c_int, st],
             "drc_krum_select": [C.POINTER(KrumSelectArgs), st],
             "drc_gemm_bf16": [ptr, i64, C.c_int, ptr, i64, C.c_int, ptr, i64, C.c_int, C.c_int, C.c_int, C.c_int, ptr, ptr,
-                              C.c_int, C.c_int, C.c_int, C.c_int, st],
+                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, st],
             "drc_rt_init": [C.c_int],
             "drc_rt_granularity": [C.c_int, C.POINTER(u64)],
             "drc_rt_alloc": [C.c_int, u64, C.POINTER(ptr), C.POINTER(u64), C.POINTER(C.c_int)],

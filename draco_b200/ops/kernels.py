@@ -244,7 +244,7 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: boo
     bias_b16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
     code = N.cuda().drc_gemm_bf16(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), out.data_ptr(),
                                   out.stride(0), int(out.dtype == torch.float32), M, Nn, K, bias_f32, bias_b16, int(relu),
-                                  int(accumulate), block_n, sm_count(A.device), _stream())
+                                  int(accumulate), block_n, sm_count(A.device), A.device.index, _stream())
     N.check(code, "gemm_bf16")
     return out
 

@@ -32,29 +32,21 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         from . import kernels as K
+        # x is 2-d and contiguous (Linear.forward flattens outside the Function so the output is never a view)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        x2 = x.reshape(-1, x.shape[-1])
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
-        if K.gemm_supported(x2, weight) and weight.is_contiguous():
+        if K.gemm_supported(x, weight) and weight.is_contiguous():
             backend_counters["tcgen05"] += 1
-            y = K.gemm_bf16(x2, weight, bias=bias)
-        else:
-            backend_counters["aten"] += 1
-            y = F.linear(x2, weight, bias)
-        return y.reshape(*x.shape[:-1], weight.shape[0])
+            return K.gemm_bf16(x, weight, bias=bias)
+        backend_counters["aten"] += 1
+        return F.linear(x, weight, bias)
 
     @staticmethod
     def backward(ctx, dy):
         from . import kernels as K
         x, weight = ctx.saved_tensors
-        dy2 = dy.reshape(-1, dy.shape[-1])
-        if not dy2.is_contiguous():
-            dy2 = dy2.contiguous()
-        x2 = x.reshape(-1, x.shape[-1])
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
+        dy2 = dy if dy.is_contiguous() else dy.contiguous()
+        x2 = x
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             if K.gemm_supported(dy2, weight) and weight.shape[1] >= 64:
@@ -63,7 +55,6 @@ class _LinearFn(torch.autograd.Function):
             else:
                 backend_counters["aten"] += 1
                 dx = dy2 @ weight
-            dx = dx.reshape(x.shape)
         if ctx.needs_input_grad[1]:
             if K.gemm_supported(dy2, x2) and x2.shape[1] >= 64:
                 backend_counters["tcgen05"] += 1
@@ -94,7 +85,11 @@ class Linear(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if _use_native(x) and self.weight.dtype == torch.bfloat16:
-            return _LinearFn.apply(x, self.weight, self.bias)
+            x2 = x.reshape(-1, x.shape[-1])
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            y = _LinearFn.apply(x2, self.weight, self.bias)
+            return y if x.dim() == 2 else y.reshape(*x.shape[:-1], self.out_features)
         return F.linear(x, self.weight, self.bias)
 
     def extra_repr(self) -> str:

@@ -60,6 +60,7 @@ class FusedEngine:
         self.kernels_per_step = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._use_graph = cfg.cuda_graphs and cfg.err_mode != "omniscient"
+        self._eager_steps = 0
 
         if cfg.deterministic:
             torch.backends.cudnn.deterministic = True
@@ -190,24 +191,13 @@ class FusedEngine:
         return n
 
     def _capture(self) -> None:
-        # honour the "omniscient needs the host step" restriction
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            # warm-up outside capture: lazy cuDNN/cuBLAS init must not happen while capturing.  The warm-up runs the
-            # real step 1 and 2 (they count as training steps).
-            for _ in range(2):
-                self._stage(self.step)
-                self.kernels_per_step = self._enqueue_local_step(self.step)
-                self.step += 1
-        torch.cuda.current_stream().wait_stream(s)
+        """Capture this process's whole step once; replays then advance the device-side step counter themselves.
+        (Called after two eager steps so that lazy cuDNN / cuBLAS initialisation never happens under capture.)"""
         torch.cuda.synchronize()
         self._check_error()
         self.graph = torch.cuda.CUDAGraph()
-        self._stage(self.step)
         with torch.cuda.graph(self.graph):
             self.kernels_per_step = self._enqueue_local_step(None)
-        # capture does not execute: nothing to account for
 
     def _stage(self, step: int) -> int:
         if self.local_workers and self.worker.dataset is not None:
@@ -215,20 +205,21 @@ class FusedEngine:
         return 0
 
     def train_step(self, stage: bool = True) -> None:
-        """Enqueue one full step for this process (asynchronous; call ``read_metrics``/``synchronize`` to wait)."""
+        """Enqueue exactly one full step for this process (asynchronous; ``read_metrics``/``synchronize`` wait).
+        With CUDA graphs the first two steps run eagerly, the third call captures, and from then on a step is one
+        graph replay (plus the input staging copies)."""
         if not self.active:
             self.step += 1
             return
-        if self._use_graph:
-            if self.graph is None:
-                self._capture()
-            if stage:
-                self._stage(self.step)
+        if self._use_graph and self.graph is None and self._eager_steps >= 2:
+            self._capture()
+        if stage:
+            self._stage(self.step)
+        if self.graph is not None:
             self.graph.replay()
         else:
-            if stage:
-                self._stage(self.step)
             self.kernels_per_step = self._enqueue_local_step(self.step)
+            self._eager_steps += 1
         self.step += 1
 
     # ------------------------------------------------------------------ host-visible results

@@ -199,7 +199,7 @@ def test_update_matches_torch_sgd_over_steps(K, dev):
 @pytest.mark.parametrize("n,s,liars", [(7, 2, (1, 4)), (7, 2, ()), (7, 3, (0, 2, 6)), (7, 1, (3,)), (5, 2, (4,))])
 def test_cyclic_decode_kernels(K, dev, n, s, liars):
     code = cyclic.search_w(n, s)
-    L = small_layout()
+    L = ArenaLayout.from_model(build_model("LeNet"), bf16=False, channels_last=True)     # fp32 gradient streams only
     Gm = fill_valid(L, n, dev, seed=4, scale=0.05)
     step, cnt, flags = ctrl(dev, 1)
     R = torch.zeros(n, 2 * L.total, device=dev)

@@ -13,6 +13,10 @@ for s in $STAGES; do
     engine)  timeout -k 10 900 python -m pytest tests/test_fused_engine_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/t_engine.log 2>&1; echo "engine rc=$?" ;;
     bench)   timeout -k 10 600 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench1.log 2>&1; echo "bench rc=$?" ;;
     benchnccl) timeout -k 10 600 python bench.py --gpus 1 --steps 10 --warmup 3 --impl nccl > gpurun_out/bench1_nccl.log 2>&1; echo "benchnccl rc=$?" ;;
+    gemmbench) timeout -k 10 600 python tools/bench_gemm.py --json gpurun_out/gemm_bench.json > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
+    ncu_gemm) timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 6 -c 2 -f -o gpurun_out/prof_gemm python tools/bench_gemm.py --quick > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
+    ncu_step) timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"push_encode|vote_compare|aggregate_update" -s 9 -c 3 -f -o gpurun_out/prof_step python tools/prof_step.py > gpurun_out/ncu_step.log 2>&1; echo "ncu_step rc=$?" ;;
+    launches) STEPS=3 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/prof_step.py > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
     alltests) timeout -k 10 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "alltests rc=$?" ;;
   esac
 done
