@@ -123,7 +123,13 @@ class BatchPlan:
     redundancy: int = 1                       # cyclic: 2s+1
 
     def _perm(self, seed: int) -> np.ndarray:
-        return np.random.RandomState(seed & 0x7FFFFFFF).permutation(self.dataset_size)
+        cache = self.__dict__.setdefault("_perm_cache", {})
+        key = seed & 0x7FFFFFFF
+        if key not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = np.random.RandomState(key).permutation(self.dataset_size)
+        return cache[key]
 
     def _slice(self, perm: np.ndarray, pos: int, width: int) -> np.ndarray:
         start = (pos * width) % max(self.dataset_size - width + 1, 1)

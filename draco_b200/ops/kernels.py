@@ -61,9 +61,12 @@ def push_encode(layout: ArenaLayout, g32: Sequence[Addr], g16: Sequence[Addr], d
     a = N.PushArgs()
     R = len(g32)
     assert 1 <= R <= N.MAX_R
+    needs_bf16 = any(sp.is_bf16 for sp in layout.specs)
     for k in range(R):
         a.g32[k] = addr(g32[k])
         a.g16[k] = addr(g16[k]) if g16 and g16[k] is not None else None
+        if needs_bf16 and not a.g16[k]:
+            raise ValueError("layout has bf16 tensors: push_encode needs the bf16 gradient arena of every stream")
     a.R = R
     a.cyclic = 1 if coef is not None else 0
     if coef is not None:

@@ -61,6 +61,7 @@ class FusedEngine:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._use_graph = cfg.cuda_graphs and cfg.err_mode != "omniscient"
         self._eager_steps = 0
+        self._staged_step = -1
 
         if cfg.deterministic:
             torch.backends.cudnn.deterministic = True
@@ -213,7 +214,7 @@ class FusedEngine:
             return
         if self._use_graph and self.graph is None and self._eager_steps >= 2:
             self._capture()
-        if stage:
+        if stage and self._staged_step != self.step:
             self._stage(self.step)
         if self.graph is not None:
             self.graph.replay()
@@ -221,6 +222,11 @@ class FusedEngine:
             self.kernels_per_step = self._enqueue_local_step(self.step)
             self._eager_steps += 1
         self.step += 1
+        if stage:
+            # prefetch: gather the next step's batches on the CPU while the GPU runs this step; the H2D copies are
+            # stream-ordered after the step that was just enqueued, so they cannot overwrite inputs still in use
+            self._stage(self.step)
+            self._staged_step = self.step
 
     # ------------------------------------------------------------------ host-visible results
     def _check_error(self) -> None:

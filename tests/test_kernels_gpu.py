@@ -308,7 +308,7 @@ def test_cast_and_flag_kernels(K, dev):
 
 def test_cross_stream_flag_handshake(K, dev):
     """Producer and consumer on different streams synchronise only through the flag word."""
-    L = small_layout()
+    L = small_layout(bf16_some=False)
     g32 = fill_valid(L, 1, dev, seed=14)[0]
     dst = torch.zeros(L.total, device=dev)
     out = torch.zeros(L.total, device=dev)
