@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..ops.linear import Linear
+from ..ops.norm import FusedBatchNorm2d
 from .split import make_split
 
 
@@ -31,18 +32,18 @@ class BasicBlock(nn.Module):
     def __init__(self, in_planes: int, planes: int, stride: int = 1) -> None:
         super().__init__()
         self.conv1 = _conv(in_planes, planes, 3, stride)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = FusedBatchNorm2d(planes)
         self.conv2 = _conv(planes, planes, 3)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = FusedBatchNorm2d(planes)
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != planes * self.expansion:
             self.shortcut = nn.Sequential(_conv(in_planes, planes * self.expansion, 1, stride),
-                                          nn.BatchNorm2d(planes * self.expansion))
+                                          FusedBatchNorm2d(planes * self.expansion))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return F.relu(out + self.shortcut(x))
+        out = self.bn1(self.conv1(x), relu=True)
+        # bn2 + shortcut add + relu in one pass (ops/norm.py)
+        return self.bn2(self.conv2(out), residual=self.shortcut(x), relu=True)
 
 
 class Bottleneck(nn.Module):
@@ -51,21 +52,20 @@ class Bottleneck(nn.Module):
     def __init__(self, in_planes: int, planes: int, stride: int = 1) -> None:
         super().__init__()
         self.conv1 = _conv(in_planes, planes, 1)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = FusedBatchNorm2d(planes)
         self.conv2 = _conv(planes, planes, 3, stride)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = FusedBatchNorm2d(planes)
         self.conv3 = _conv(planes, planes * self.expansion, 1)
-        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        self.bn3 = FusedBatchNorm2d(planes * self.expansion)
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != planes * self.expansion:
             self.shortcut = nn.Sequential(_conv(in_planes, planes * self.expansion, 1, stride),
-                                          nn.BatchNorm2d(planes * self.expansion))
+                                          FusedBatchNorm2d(planes * self.expansion))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = F.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        return F.relu(out + self.shortcut(x))
+        out = self.bn1(self.conv1(x), relu=True)
+        out = self.bn2(self.conv2(out), relu=True)
+        return self.bn3(self.conv3(out), residual=self.shortcut(x), relu=True)
 
 
 class ResNet(nn.Module):
@@ -76,7 +76,7 @@ class ResNet(nn.Module):
         self.num_classes = num_classes
         self.in_planes = 64
         self.conv1 = _conv(3, 64, 3)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.bn1 = FusedBatchNorm2d(64)
         self.layer1 = self._make_layer(block, 64, num_blocks[0], 1)
         self.layer2 = self._make_layer(block, 128, num_blocks[1], 2)
         self.layer3 = self._make_layer(block, 256, num_blocks[2], 2)
@@ -91,7 +91,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn1(self.conv1(x), relu=True)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
         out = F.adaptive_avg_pool2d(out, 1) if out.shape[-1] != 4 else F.avg_pool2d(out, 4)
         return self.linear(out.flatten(1))

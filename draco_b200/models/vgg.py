@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from ..ops.linear import Linear
+from ..ops.norm import FusedBatchNorm2d
 from .split import make_split
 
 CFG = {
@@ -38,8 +39,11 @@ def make_layers(cfg: List[Union[int, str]], batch_norm: bool = False) -> nn.Sequ
             continue
         layers.append(nn.Conv2d(cin, int(v), kernel_size=3, padding=1))
         if batch_norm:
-            layers.append(nn.BatchNorm2d(int(v)))
-        layers.append(nn.ReLU(inplace=True))
+            # BN + ReLU fused (ops/norm.py); the Identity keeps torchvision's module numbering / state_dict keys
+            layers.append(FusedBatchNorm2d(int(v), relu=True))
+            layers.append(nn.Identity())
+        else:
+            layers.append(nn.ReLU(inplace=True))
         cin = int(v)
     return nn.Sequential(*layers)
 

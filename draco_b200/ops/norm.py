@@ -1,0 +1,126 @@
+"""BatchNorm2d with fused residual-add + ReLU on the sm_100a kernels of ``csrc/cuda/bn_fused.cu``.
+
+``FusedBatchNorm2d`` *is* an ``nn.BatchNorm2d`` (same parameters, buffers and state_dict keys as the reference's models,
+src/model_ops/resnet.py:19-24) whose ``forward(x, residual=None, relu=False)`` computes
+``relu?(batch_norm(x) + residual)``.  On CUDA, in training mode, for bf16 channels-last activations with a power-of-two
+channel count it runs as two streaming kernels per direction (statistics / apply, reduce / apply) with deterministic
+reductions; everywhere else it is exactly ``F.batch_norm`` (+ add, + relu) so CPU runs and evaluation are unchanged.
+``backend_counters`` records which path served each call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import _native as N
+
+backend_counters = {"fused": 0, "aten": 0}
+_counter_cache = {}
+
+
+def _lib():
+    lib = N.cuda()
+    if not getattr(lib, "_bn_ready", False):
+        st = N.ptr
+        lib.drc_bn_supported.argtypes = [C.c_int]
+        lib.drc_bn_supported.restype = C.c_int
+        lib.drc_bn_workspace.argtypes = [N.i64, C.c_int, C.c_int]
+        lib.drc_bn_workspace.restype = N.i64
+        lib.drc_bn_fwd.argtypes = [N.ptr] * 11 + [N.i64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, st]
+        lib.drc_bn_fwd.restype = C.c_int
+        lib.drc_bn_bwd.argtypes = [N.ptr] * 13 + [N.i64, C.c_int, C.c_int, C.c_int, st]
+        lib.drc_bn_bwd.restype = C.c_int
+        lib._bn_ready = True
+    return lib
+
+
+def _counter(device: torch.device) -> torch.Tensor:
+    if device not in _counter_cache:
+        _counter_cache[device] = torch.zeros(4, dtype=torch.int32, device=device)
+    return _counter_cache[device]
+
+
+def _sms(device: torch.device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def fused_supported(x: torch.Tensor, training: bool) -> bool:
+    return (training and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and
+            x.is_contiguous(memory_format=torch.channels_last) and os.environ.get("DRACO_BN", "fused") == "fused" and
+            bool(_lib().drc_bn_supported(x.shape[1])))
+
+
+class _BnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu):
+        lib = _lib()
+        n, c, h, w = x.shape
+        M = n * h * w
+        dev = x.device
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        mean = torch.empty(c, dtype=torch.float32, device=dev)
+        invstd = torch.empty(c, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.drc_bn_workspace(M, c, _sms(dev))), dtype=torch.float32, device=dev)
+        if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
+            residual = residual.contiguous(memory_format=torch.channels_last)
+        N.check(lib.drc_bn_fwd(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
+                               _p(running_var), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), _counter(dev).data_ptr(),
+                               M, c, float(eps), float(momentum), int(relu), _sms(dev),
+                               torch.cuda.current_stream().cuda_stream), "bn_fwd")
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, invstd)
+        ctx.relu, ctx.has_res = bool(relu), residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib()
+        x, y, gamma, mean, invstd = ctx.saved_tensors
+        n, c, h, w = x.shape
+        M = n * h * w
+        dev = x.device
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.drc_bn_workspace(M, c, _sms(dev))), dtype=torch.float32, device=dev)
+        torch.cuda.set_device(dev)
+        N.check(lib.drc_bn_bwd(dy.data_ptr(), _p(y), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                               dx.data_ptr(), _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), sums.data_ptr(),
+                               _counter(dev)[1:].data_ptr(), M, c, int(ctx.relu), _sms(dev),
+                               torch.cuda.current_stream().cuda_stream), "bn_bwd")
+        return dx, dres, dgamma, dbeta, None, None, None, None, None
+
+
+class FusedBatchNorm2d(nn.BatchNorm2d):
+    """``nn.BatchNorm2d`` + optional fused residual add and ReLU."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, relu: bool = False):
+        super().__init__(num_features, eps=eps, momentum=momentum)
+        self.fuse_relu = relu
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None) -> torch.Tensor:
+        relu = self.fuse_relu if relu is None else relu
+        if (self.weight.dtype == torch.float32 and self.track_running_stats and fused_supported(x, self.training)
+                and (residual is None or residual.shape == x.shape)):
+            backend_counters["fused"] += 1
+            if self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(1)
+            return _BnActFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                  self.momentum if self.momentum is not None else 0.1, relu)
+        backend_counters["aten"] += 1
+        y = super().forward(x)
+        if residual is not None:
+            y = y + residual
+        return F.relu(y) if relu else y
