@@ -28,6 +28,7 @@ struct PushArgs {
   unsigned int* done_counter;             // local, zero
   unsigned long long* flag;               // peer pointer: PS-side grad_ready[worker]
   float* local_copy;                      // optional local fp32 copy of what was sent (debug / NCCL path), may be null
+  int tile_begin, tile_end;               // bucket of tiles to push (tile_end == 0: up to the end of the arena)
 };
 
 // counter-based normal generator (Philox-lite: 2 rounds of a 64-bit mix, Box-Muller) keyed by (seed, step, worker, idx)
@@ -59,7 +60,11 @@ __global__ void __launch_bounds__(DRC_THREADS) push_encode_kernel(const __grid_c
                    ((a.adv_bitmap[step % (unsigned long long)a.adv_len] >> a.worker) & 1u);
   const unsigned long long key = mix64(a.seed ^ (step << 8) ^ (unsigned long long)a.worker);
 
-  for (int tile = blockIdx.x; tile < a.tv.ntiles; tile += gridDim.x) {
+  // [tile_begin, tile_end): a bucket of the arena.  Buckets are pushed as soon as backprop has finished the layers they
+  // cover, on a side stream, so the transfer overlaps the rest of the backward pass (the reference's "send layer l while
+  // back-propagating layer l-1", src/model_ops/resnet_split.py:431-623); only the last bucket carries the flag.
+  const int tile_end = a.tile_end > 0 ? a.tile_end : a.tv.ntiles;
+  for (int tile = a.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     int tensor;
     const int valid = tile_valid(a.tv, tile, tensor);
     const int is_bf16 = a.tv.meta[tensor].is_bf16;

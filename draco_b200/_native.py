@@ -50,7 +50,8 @@ class PushArgs(C.Structure):
     _fields_ = [("g32", ptr * MAX_R), ("g16", ptr * MAX_R), ("coef_re", C.c_float * MAX_R), ("coef_im", C.c_float * MAX_R),
                 ("R", C.c_int), ("cyclic", C.c_int), ("dst", ptr), ("tv", TileView), ("adv_bitmap", ptr),
                 ("adv_len", C.c_int), ("step_ptr", ptr), ("worker", C.c_int), ("attack", C.c_int),
-                ("magnitude", C.c_float), ("seed", u64), ("done_counter", ptr), ("flag", ptr), ("local_copy", ptr)]
+                ("magnitude", C.c_float), ("seed", u64), ("done_counter", ptr), ("flag", ptr), ("local_copy", ptr),
+                ("tile_begin", C.c_int), ("tile_end", C.c_int)]
 
 
 class OmniArgs(C.Structure):

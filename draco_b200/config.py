@@ -60,6 +60,7 @@ class JobConfig:
     spin_timeout_s: float = 60.0
     num_classes: int = 10
     deterministic: bool = True
+    overlap_push: bool = True       # ship gradient buckets while the remaining layers are still back-propagating
 
     # ---- derived --------------------------------------------------------------------------
     def resolve(self, world_size: int) -> "JobConfig":
@@ -144,6 +145,7 @@ def add_fit_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
     a("--multicast", type=str, default="auto", choices=("auto", "on", "off"))
     a("--spin-timeout-s", type=float, default=d.spin_timeout_s)
     a("--num-classes", type=int, default=10)
+    a("--no-overlap-push", dest="overlap_push", action="store_false", default=True)
     return parser
 
 

@@ -55,9 +55,9 @@ def _flag_list(flags: Sequence[Addr]) -> N.FlagList:
 def push_encode(layout: ArenaLayout, g32: Sequence[Addr], g16: Sequence[Addr], dst: Addr, *, step_ptr: Addr,
                 worker: int, done_counter: Addr, flag: Addr = None, coef: Optional[Sequence[complex]] = None,
                 adv_bitmap: Addr = None, adv_len: int = 0, attack: int = 0, magnitude: float = -100.0, seed: int = 428,
-                local_copy: Addr = None, grid: Optional[int] = None) -> None:
+                local_copy: Addr = None, grid: Optional[int] = None, tile_range: Optional[tuple] = None) -> None:
     """Fused encode + adversary + store into ``dst`` (a peer pointer) + release flag.  ``coef`` given => cyclic encode
-    of ``len(coef)`` gradient streams into an interleaved complex64 slot."""
+    of ``len(coef)`` gradient streams into an interleaved complex64 slot.  ``tile_range=(t0, t1)`` pushes one bucket."""
     a = N.PushArgs()
     R = len(g32)
     assert 1 <= R <= N.MAX_R
@@ -87,7 +87,11 @@ def push_encode(layout: ArenaLayout, g32: Sequence[Addr], g16: Sequence[Addr], d
     a.done_counter = addr(done_counter)
     a.flag = addr(flag)
     a.local_copy = addr(local_copy)
-    N.check(N.cuda().drc_push_encode(C.byref(a), grid or stream_grid(layout), _stream()), "push_encode")
+    ntiles = layout.ntiles
+    if tile_range is not None:
+        a.tile_begin, a.tile_end = int(tile_range[0]), int(tile_range[1])
+        ntiles = a.tile_end - a.tile_begin
+    N.check(N.cuda().drc_push_encode(C.byref(a), grid or max(1, min(ntiles, sm_count() * 8)), _stream()), "push_encode")
 
 
 def omniscient(grad_in: Addr, slot_stride: int, honest_mask: int, worker: int, magnitude: float, total: int, *,

@@ -61,6 +61,8 @@ class FusedEngine:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._use_graph = cfg.cuda_graphs and cfg.err_mode != "omniscient"
         self._eager_steps = 0
+        self.overlap_push = cfg.overlap_push and not self.cyclic
+        self.push_stream = torch.cuda.Stream(device=device) if self.overlap_push else None
         self._staged_step = -1
 
         if cfg.deterministic:
@@ -160,12 +162,35 @@ class FusedEngine:
                 # liars read the honest slots: on a shared stream the honest workers must be enqueued first
                 order.sort(key=lambda r: self.schedule.is_adversary(r, step_host))
             for w in order:
-                wc.forward_backward(w, step_host)
                 g32 = [g[0] for g in wc.grads]
                 g16 = [g[1] for g in wc.grads]
                 coef = list(self.code.coeffs_of(w - 1)) if self.cyclic else None
                 lying_now = (step_host is not None and cfg.err_mode == "omniscient"
                              and self.schedule.is_adversary(w, step_host))
+                push_kw = dict(step_ptr=self.step_dev, worker=w - 1, done_counter=self.counters[1:2], coef=coef,
+                               adv_bitmap=self.adv_bitmap, adv_len=len(self.schedule.ranks),
+                               attack=self.attack if self.attack != 4 else 0, magnitude=cfg.attack_magnitude, seed=cfg.seed)
+                if self.overlap_push and not lying_now:
+                    # bucketed push on a side stream, overlapped with the rest of the backward pass
+                    state = {"done": 0}
+                    nb = len(wc.buckets)
+
+                    def on_bucket(b, _w=w, _state=state, _g32=g32, _g16=g16, _kw=push_kw):
+                        t0, t1, _ = wc.buckets[b]
+                        _state["done"] += 1
+                        ev = torch.cuda.Event()
+                        ev.record()                                   # on the backward stream (autograd thread)
+                        with torch.cuda.stream(self.push_stream):
+                            self.push_stream.wait_event(ev)
+                            K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1),
+                                          flag=self.grad_flag_ptr(_w) if _state["done"] == nb else None, **_kw)
+
+                    wc.forward_backward(w, step_host, on_bucket=on_bucket)
+                    assert state["done"] == nb, "a gradient bucket never became ready"
+                    torch.cuda.current_stream().wait_stream(self.push_stream)      # join (also required by capture)
+                    n += nb
+                    continue
+                wc.forward_backward(w, step_host)
                 if lying_now:
                     honest = 0
                     for h in range(1, self.P + 1):
@@ -177,11 +202,7 @@ class FusedEngine:
                                  step_ptr=self.step_dev, done_counter=self.counters[1:2], flag=self.grad_flag_ptr(w))
                     n += 2
                 else:
-                    K.push_encode(L, g32, g16, self.slot_ptr(w), step_ptr=self.step_dev, worker=w - 1,
-                                  done_counter=self.counters[1:2], flag=self.grad_flag_ptr(w), coef=coef,
-                                  adv_bitmap=self.adv_bitmap, adv_len=len(self.schedule.ranks),
-                                  attack=self.attack if self.attack != 4 else 0, magnitude=cfg.attack_magnitude,
-                                  seed=cfg.seed)
+                    K.push_encode(L, g32, g16, self.slot_ptr(w), flag=self.grad_flag_ptr(w), **push_kw)
                     n += 1
         if self.is_ps:
             flags = [self.flagsB.data_ptr() + i * FLAG_STRIDE for i in range(self.P)]

@@ -32,6 +32,27 @@ def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1, 5)) -> List[to
     return [correct[:min(k, maxk)].reshape(-1).float().sum() * (100.0 / target.shape[0]) for k in topk]
 
 
+def plan_buckets(layout: ArenaLayout, nbuckets: int = 4):
+    """Split the arena into ``<= nbuckets`` contiguous tile ranges of similar size, returned in the order backprop
+    finishes them (last layers first): ``[(tile_begin, tile_end, [param indices]), ...]``."""
+    from .arena import TILE
+    total = layout.ntiles
+    target = max(total // max(nbuckets, 1), 1)
+    buckets, cur, cur_tiles = [], [], 0
+    end_tile = total
+    for i in range(layout.ntensors - 1, -1, -1):
+        s = layout.specs[i]
+        cur.append(i)
+        cur_tiles += (s.numel + TILE - 1) // TILE
+        if cur_tiles >= target and len(buckets) < nbuckets - 1 and i > 0:
+            begin = s.offset // TILE
+            buckets.append((begin, end_tile, cur))
+            end_tile, cur, cur_tiles = begin, [], 0
+    if cur:
+        buckets.append((0, end_tile, cur))
+    return buckets
+
+
 def make_model(cfg: JobConfig) -> torch.nn.Module:
     torch.manual_seed(cfg.seed)
     kwargs = {}
@@ -52,6 +73,14 @@ class WorkerCompute:
         self.binder = ModelBinder(self.model, self.layout, self.device, self.bf16, params_f32)
         self.R = cfg.redundancy if cfg.approach == "cyclic" else 1
         self.grads: List[Tuple[torch.Tensor, Optional[torch.Tensor]]] = [self.binder.new_grad_arenas() for _ in range(self.R)]
+        # gradient buckets (contiguous tile ranges, listed in the order backprop completes them) + readiness hooks:
+        # the transport can ship a bucket while the remaining layers are still back-propagating
+        self.buckets = plan_buckets(self.layout, 4)
+        self._param_bucket = {i: b for b, (_, _, idxs) in enumerate(self.buckets) for i in idxs}
+        self._bucket_left: List[int] = []
+        self._bucket_cb = None
+        for i, p in enumerate(self.binder.params):
+            p.register_post_accumulate_grad_hook(self._make_ready_hook(i))
         self.model.train()
         self.has_dropout = any(isinstance(m, torch.nn.Dropout) for m in self.model.modules())
         c, h, w = self.model.input_shape if hasattr(self.model, "input_shape") else (3, 32, 32)
@@ -151,9 +180,22 @@ class WorkerCompute:
             x = x.contiguous(memory_format=torch.channels_last)
         return x
 
-    def forward_backward(self, wk: int, step_host: Optional[int] = None) -> None:
+    def _make_ready_hook(self, i: int):
+        def hook(_param):
+            cb = self._bucket_cb
+            if cb is None:
+                return
+            b = self._param_bucket[i]
+            self._bucket_left[b] -= 1
+            if self._bucket_left[b] == 0:
+                cb(b)
+        return hook
+
+    def forward_backward(self, wk: int, step_host: Optional[int] = None, on_bucket=None) -> None:
         """Run fwd/bwd for all sub-batches of logical worker ``wk``; gradients land in ``self.grads[k]``.
-        Everything enqueued here is capturable in a CUDA graph (no host sync)."""
+        Everything enqueued here is capturable in a CUDA graph (no host sync).  ``on_bucket(b)`` is called (from the
+        autograd thread, on the backward stream) as soon as every gradient of bucket ``b`` is final -- only during the
+        last sub-batch, i.e. when the values in the arenas are what will be sent."""
         met = self.metrics[wk]
         met.zero_()
         ids = self.plan.batch_ids(step_host or 1, wk) if self.has_dropout else None
@@ -170,10 +212,16 @@ class WorkerCompute:
             y = self.y[wk][k]
             out = self.model(x)
             loss = F.cross_entropy(out.float(), y)
-            if hasattr(self.model, "backward_single"):
-                self.model.backward_single(loss)
-            else:
-                loss.backward()
+            if on_bucket is not None and k == self.R - 1:
+                self._bucket_left = [len(idxs) for _, _, idxs in self.buckets]
+                self._bucket_cb = on_bucket
+            try:
+                if hasattr(self.model, "backward_single"):
+                    self.model.backward_single(loss)
+                else:
+                    loss.backward()
+            finally:
+                self._bucket_cb = None
             with torch.no_grad():
                 p1, p5 = accuracy(out.detach(), y)
                 met += torch.stack([loss.detach(), p1, p5]) / self.R

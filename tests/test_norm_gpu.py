@@ -87,27 +87,44 @@ def test_fused_bn_is_deterministic_and_eval_falls_back():
 
 
 def test_resnet18_fused_vs_aten_training_step():
-    """Whole-model check: one bf16 ResNet-18 fwd/bwd with the fused BN kernels vs the ATen path."""
+    """Whole-model check: one bf16 ResNet-18 fwd/bwd with the fused BN kernels is as close to the fp32 model as the ATen
+    bf16 path is (bf16 noise through 20 layers makes the two bf16 runs differ from each other by design)."""
     import os
     from draco_b200.models import ResNet18
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    x = torch.randn(32, 3, 32, 32, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    y = torch.randint(0, 10, (32,), device=dev)
-    res = {}
-    for mode in ("fused", "aten"):
-        os.environ["DRACO_BN"] = mode
+    x32 = torch.randn(64, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (64,), device=dev)
+
+    def run(mode):
         torch.manual_seed(1)
         m = ResNet18().to(dev)
-        for mod in m.modules():
-            if not isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
-                for p in mod.parameters(recurse=False):
-                    p.data = p.data.to(torch.bfloat16)
+        xin = x32
+        if mode != "fp32":
+            os.environ["DRACO_BN"] = mode
+            for mod in m.modules():
+                if not isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                    for p in mod.parameters(recurse=False):
+                        p.data = p.data.to(torch.bfloat16)
+            xin = x32.to(torch.bfloat16)
         m = m.to(memory_format=torch.channels_last)
-        loss = F.cross_entropy(m(x).float(), y)
+        loss = F.cross_entropy(m(xin.contiguous(memory_format=torch.channels_last)).float(), y)
         loss.backward()
-        res[mode] = (float(loss), m.conv1.weight.grad.float().clone(), m.layer4[1].bn2.weight.grad.clone())
+        return float(loss), [p.grad.detach().float().clone() for p in m.parameters()]
+
+    from draco_b200.ops.norm import backend_counters
+    ref_loss, ref_g = run("fp32")
+    before = backend_counters["fused"]
+    f_loss, f_g = run("fused")
+    assert backend_counters["fused"] - before == 20, "all 20 BatchNorm layers of ResNet-18 should take the fused path"
+    a_loss, a_g = run("aten")
     os.environ["DRACO_BN"] = "fused"
-    assert abs(res["fused"][0] - res["aten"][0]) < 0.08
-    g1, g2 = res["fused"][1], res["aten"][1]
-    assert float((g1 - g2).norm() / g2.norm()) < 0.15
+
+    def rel(gs):
+        num = sum(float((g - r).norm() ** 2) for g, r in zip(gs, ref_g)) ** 0.5
+        den = sum(float(r.norm() ** 2) for r in ref_g) ** 0.5
+        return num / den
+
+    ef, ea = rel(f_g), rel(a_g)
+    assert abs(f_loss - ref_loss) < 0.05 and abs(a_loss - ref_loss) < 0.05
+    assert ef < 1.5 * ea + 0.02, (ef, ea)

@@ -17,7 +17,10 @@ for s in $STAGES; do
     ncu_gemm) timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 6 -c 2 -f -o gpurun_out/prof_gemm python tools/bench_gemm.py --quick > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
     ncu_step) timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"push_encode|vote_compare|aggregate_update" -s 9 -c 3 -f -o gpurun_out/prof_step python tools/prof_step.py > gpurun_out/ncu_step.log 2>&1; echo "ncu_step rc=$?" ;;
     launches) STEPS=3 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/prof_step.py > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
+    worker) timeout -k 10 600 python tools/bench_worker.py > gpurun_out/bench_worker.log 2>&1; echo "worker rc=$?" ;;
+    diag) timeout -k 10 120 python tools/diag_flags.py > gpurun_out/diag_flags.log 2>&1; echo "diag rc=$?" ;;
+    norm) timeout -k 10 300 python -m pytest tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/t_norm.log 2>&1; echo "norm rc=$?" ;;
     alltests) timeout -k 10 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "alltests rc=$?" ;;
   esac
 done
-tail -n 25 gpurun_out/t_*.log gpurun_out/bench*.log 2>/dev/null | tail -n 150
+tail -n 25 gpurun_out/t_*.log gpurun_out/bench*.log gpurun_out/diag*.log 2>/dev/null | cut -c1-1200 | tail -n 150
