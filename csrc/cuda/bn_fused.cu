@@ -1,18 +1,17 @@
 // K10 (normalisation part): fused training-mode BatchNorm + residual add + ReLU for NHWC bf16 activations.
 //
-// A launch list of the flagship step (profiles/launches_r1.md) shows ATen's channels-last BatchNorm kernels and the
-// separate ReLU / add / threshold_backward passes taking ~60 % of a worker's forward+backward while running at 5-30 %
-// of HBM bandwidth.  These kernels do the same math in the minimum number of passes with 16-byte accesses:
+// The activations of the CIFAR models are small (2-17 MB per tensor at B=128) and usually still L2-resident when the
+// normalisation runs, so these kernels are latency-bound, not bandwidth-bound: what matters is memory-level parallelism
+// and a short reduction tail.  Design (second iteration, see profiles/bn_fused.md for the measurements that drove it):
 //
-//   forward   bn_stats_kernel     : read x           -> per-channel mean / invstd (+ running statistics)
-//             bn_apply_kernel     : read x (+res)    -> y = relu?( gamma * (x - mean) * invstd + beta (+ res) )
-//   backward  bn_bwd_reduce_kernel: read dy, y, x    -> dgamma, dbeta (ReLU mask recomputed from y > 0)
-//             bn_bwd_apply_kernel : read dy, y, x    -> dx (and d_residual)
-//
-// x is viewed as [M = N*H*W][C]; a thread owns 8 consecutive channels (one 16-byte word) and walks rows, so every
-// access is a full-width coalesced vector.  Reductions are two-stage with a FIXED summation order (per-CTA partials in
-// a workspace, the last CTA to finish folds them in index order): bit-identical results on every replica, which the
-// exact-equality majority vote requires (reference: src/master/rep_master.py:162).  No float atomics.
+//   * 1024-thread CTAs, at most one per SM, each thread owning 4 consecutive channels (8-byte accesses) of a strided
+//     set of rows with the row loop unrolled x4  -> ~32 KB of loads in flight per SM;
+//   * the grid is sized from the tensor (one CTA per ~128 KB, capped at the SM count) so that the deterministic fold of
+//     the per-CTA partials by the last CTA is <= a handful of dependent L2 round trips;
+//   * forward : bn_stats_kernel  (x -> mean, invstd, running stats)        bn_apply_kernel (x, res -> y, ReLU fused)
+//     backward: bn_bwd_reduce_kernel (dy, y, x -> dgamma, dbeta)            bn_bwd_apply_kernel (dy, y, x -> dx, dres)
+//   * every reduction has a FIXED summation order (no float atomics): replicas on different GPUs stay bit-identical,
+//     which the exact-equality majority vote requires (reference: src/master/rep_master.py:162).
 //
 // Reference counterpart: nn.BatchNorm2d / F.relu inside src/model_ops/resnet.py:14-64 and vgg.py:46-59 (PyTorch-0.3 CPU).
 #include <cuda_bf16.h>
@@ -21,7 +20,9 @@
 
 namespace {
 
-constexpr int BN_THREADS = 256;
+constexpr int BN_THREADS = 1024;
+constexpr int BN_VEC = 4;                      // channels per thread
+constexpr int BN_UNROLL = 4;
 
 struct BnFwdArgs {
   const __nv_bfloat16* x;         // [M][C]
@@ -62,39 +63,55 @@ struct BnBwdArgs {
   int relu;
 };
 
-__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+__device__ __forceinline__ void unpack4(const uint2& v, float* f) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 v;
+__device__ __forceinline__ uint2 pack4(const float* f) {
+  uint2 v;
   __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  p[0] = __floats2bfloat162_rn(f[0], f[1]);
+  p[1] = __floats2bfloat162_rn(f[2], f[3]);
   return v;
 }
-__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+__device__ __forceinline__ uint2 ldg8(const __nv_bfloat16* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
 
-// Fold the per-thread accumulators of the CTA's row groups into partial[blockIdx][which][channel], fixed order.
-template <int NACC>
-__device__ __forceinline__ void cta_fold(float (&acc)[NACC][8], float* partial_blk, int C, int tpc, int rgroups, int rg, int cv,
-                                         float* smem) {
-  // smem layout: [rgroups][NACC][C]
+extern __shared__ float bn_smem[];
+
+// CTA-level fold of per-thread accumulators acc[2][4] over the row groups into partial_blk[2][C] (fixed order).
+__device__ __forceinline__ void cta_fold(const float (&acc)[2][BN_VEC], float* partial_blk, int C, int rgroups, int rg, int cv) {
+  // smem layout: [rgroups][2][C]
 #pragma unroll
-  for (int a = 0; a < NACC; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) smem[(rg * NACC + a) * C + cv * 8 + i] = acc[a][i];
+    for (int i = 0; i < BN_VEC; ++i) bn_smem[(rg * 2 + a) * C + cv * BN_VEC + i] = acc[a][i];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < NACC * C; idx += BN_THREADS) {
-    const int a = idx / C, c = idx - a * C;
+  // all 1024 threads participate: idx = (which, c), the row groups are split into `parts` interleaved subsets
+  const int n_idx = 2 * C;
+  const int parts = BN_THREADS / n_idx > 0 ? BN_THREADS / n_idx : 1;
+  if (parts > 1) {
+    const int idx = threadIdx.x % n_idx, part = threadIdx.x / n_idx;
     float s = 0.f;
-    for (int g = 0; g < rgroups; ++g) s += smem[(g * NACC + a) * C + c];
-    partial_blk[a * C + c] = s;
+    for (int g = part; g < rgroups; g += parts) s += bn_smem[g * n_idx + idx];
+    __syncthreads();
+    bn_smem[part * n_idx + idx] = s;
+    __syncthreads();
+    if (part == 0) {
+      float t = 0.f;
+      for (int p = 0; p < parts; ++p) t += bn_smem[p * n_idx + idx];
+      partial_blk[idx] = t;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < n_idx; idx += BN_THREADS) {
+      float s = 0.f;
+      for (int g = 0; g < rgroups; ++g) s += bn_smem[g * n_idx + idx];
+      partial_blk[idx] = s;
+    }
   }
 }
 
@@ -112,46 +129,79 @@ __device__ __forceinline__ bool last_cta(unsigned int* counter) {
   return s_last != 0;
 }
 
-// Sum partial[b][which][c] over b with four interleaved accumulators (fixed order -> deterministic, 4x the MLP).
-__device__ __forceinline__ float fold_partials(const float* partial, unsigned int nblk, int C, int which, int c) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  const long long stride = 2LL * C;
-  const float* p = partial + (long long)which * C + c;
-  unsigned int b = 0;
-  for (; b + 4 <= nblk; b += 4) {
-    s0 += p[(long long)b * stride]; s1 += p[(long long)(b + 1) * stride];
-    s2 += p[(long long)(b + 2) * stride]; s3 += p[(long long)(b + 3) * stride];
+// Grid-level fold by the last CTA: out[idx] = sum_b partial[b][idx], idx in [0, 2C), fixed order, all threads busy.
+// Result is left in bn_smem[0 .. 2C).
+__device__ __forceinline__ void grid_fold(const float* partial, int C) {
+  const int n_idx = 2 * C;
+  const unsigned int nblk = gridDim.x;
+  const int parts = BN_THREADS / n_idx > 0 ? BN_THREADS / n_idx : 1;
+  __syncthreads();
+  if (parts > 1) {
+    const int idx = threadIdx.x % n_idx, part = threadIdx.x / n_idx;
+    float s0 = 0.f, s1 = 0.f;
+    unsigned int b = part;
+    for (; b + parts < nblk; b += 2 * parts) {
+      s0 += __ldcg(partial + (long long)b * n_idx + idx);
+      s1 += __ldcg(partial + (long long)(b + parts) * n_idx + idx);
+    }
+    if (b < nblk) s0 += __ldcg(partial + (long long)b * n_idx + idx);
+    bn_smem[n_idx + part * n_idx + idx] = s0 + s1;
+    __syncthreads();
+    if (part == 0) {
+      float t = 0.f;
+      for (int p = 0; p < parts; ++p) t += bn_smem[n_idx + p * n_idx + idx];
+      bn_smem[idx] = t;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < n_idx; idx += BN_THREADS) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      unsigned int b = 0;
+      for (; b + 4 <= nblk; b += 4) {
+        s0 += __ldcg(partial + (long long)b * n_idx + idx);
+        s1 += __ldcg(partial + (long long)(b + 1) * n_idx + idx);
+        s2 += __ldcg(partial + (long long)(b + 2) * n_idx + idx);
+        s3 += __ldcg(partial + (long long)(b + 3) * n_idx + idx);
+      }
+      for (; b < nblk; ++b) s0 += __ldcg(partial + (long long)b * n_idx + idx);
+      bn_smem[idx] = (s0 + s1) + (s2 + s3);
+    }
   }
-  for (; b < nblk; ++b) s0 += p[(long long)b * stride];
-  return (s0 + s1) + (s2 + s3);
+  __syncthreads();
 }
 
-extern __shared__ float bn_smem[];
+#define BN_ROW_LOOP(BODY_LOAD, BODY_USE)                                                            \
+  {                                                                                                 \
+    long long r = r0 + rg;                                                                          \
+    for (; r + (long long)(BN_UNROLL - 1) * rgroups < r1; r += (long long)BN_UNROLL * rgroups) {    \
+      _Pragma("unroll") for (int u = 0; u < BN_UNROLL; ++u) { const long long off = (r + (long long)u * rgroups) * a.C + cv * BN_VEC; BODY_LOAD }  \
+      _Pragma("unroll") for (int u = 0; u < BN_UNROLL; ++u) { const long long off = (r + (long long)u * rgroups) * a.C + cv * BN_VEC; BODY_USE }   \
+    }                                                                                               \
+    for (; r < r1; r += rgroups) {                                                                  \
+      const int u = 0; const long long off = r * a.C + cv * BN_VEC; BODY_LOAD BODY_USE              \
+    }                                                                                               \
+  }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const BnFwdArgs a) {
-  const int tpc = a.C >> 3;                         // threads per row
+__global__ void __launch_bounds__(BN_THREADS, 1) bn_stats_kernel(const BnFwdArgs a) {
+  const int tpc = a.C / BN_VEC;
   const int rgroups = BN_THREADS / tpc;
   const int cv = threadIdx.x % tpc, rg = threadIdx.x / tpc;
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   long long r1 = r0 + a.rows_per_cta; if (r1 > a.M) r1 = a.M;
-  float acc[2][8];
+  float acc[2][BN_VEC];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
-  if (rg < rgroups) {
-    for (long long r = r0 + rg; r < r1; r += rgroups) {
-      float f[8];
-      unpack8(ldg16(a.x + r * a.C + cv * 8), f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { acc[0][i] += f[i]; acc[1][i] = fmaf(f[i], f[i], acc[1][i]); }
-    }
-  }
-  cta_fold<2>(acc, a.partial + (long long)blockIdx.x * 2 * a.C, a.C, tpc, rgroups, rg, cv, bn_smem);
+  for (int i = 0; i < BN_VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  uint2 xv[BN_UNROLL];
+  BN_ROW_LOOP(
+      { xv[u] = ldg8(a.x + off); },
+      { float f[BN_VEC]; unpack4(xv[u], f);
+        _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) { acc[0][i] += f[i]; acc[1][i] = fmaf(f[i], f[i], acc[1][i]); } (void)off; })
+  cta_fold(acc, a.partial + (long long)blockIdx.x * 2 * a.C, a.C, rgroups, rg, cv);
   if (last_cta(a.counter)) {
+    grid_fold(a.partial, a.C);
     const float inv_m = 1.0f / (float)a.M;
     for (int c = threadIdx.x; c < a.C; c += BN_THREADS) {
-      const float s = fold_partials(a.partial, gridDim.x, a.C, 0, c), q = fold_partials(a.partial, gridDim.x, a.C, 1, c);
-      const float m = s * inv_m;
-      float var = fmaf(-m, m, q * inv_m);
+      const float m = bn_smem[c] * inv_m;
+      float var = fmaf(-m, m, bn_smem[a.C + c] * inv_m);
       var = var < 0.f ? 0.f : var;
       a.mean[c] = m;
       a.invstd[c] = rsqrtf(var + a.eps);
@@ -164,74 +214,56 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const BnFwdArgs a)
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const BnFwdArgs a) {
-  const int tpc = a.C >> 3;
+__global__ void __launch_bounds__(BN_THREADS, 1) bn_apply_kernel(const BnFwdArgs a) {
+  const int tpc = a.C / BN_VEC;
   const int rgroups = BN_THREADS / tpc;
   const int cv = threadIdx.x % tpc, rg = threadIdx.x / tpc;
-  float scale[8], shift[8];
+  float scale[BN_VEC], shift[BN_VEC];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = cv * 8 + i;
+  for (int i = 0; i < BN_VEC; ++i) {
+    const int c = cv * BN_VEC + i;
     const float sc = a.gamma[c] * a.invstd[c];
     scale[i] = sc;
     shift[i] = fmaf(-a.mean[c], sc, a.beta[c]);
   }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   long long r1 = r0 + a.rows_per_cta; if (r1 > a.M) r1 = a.M;
-  for (long long r = r0 + rg; r < r1; r += rgroups) {
-    const long long off = r * a.C + cv * 8;
-    float f[8];
-    unpack8(ldg16(a.x + off), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
-    if (a.res) {
-      float g[8];
-      unpack8(ldg16(a.res + off), g);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += g[i];
-    }
-    if (a.relu) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-    }
-    *reinterpret_cast<uint4*>(a.y + off) = pack8(f);
-  }
+  uint2 xv[BN_UNROLL], rv[BN_UNROLL];
+  const bool has_res = a.res != nullptr;
+  BN_ROW_LOOP(
+      { xv[u] = ldg8(a.x + off); if (has_res) rv[u] = ldg8(a.res + off); },
+      { float f[BN_VEC]; unpack4(xv[u], f);
+        _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
+        if (has_res) { float g[BN_VEC]; unpack4(rv[u], g); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) f[i] += g[i]; }
+        if (a.relu) { _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) f[i] = fmaxf(f[i], 0.f); }
+        *reinterpret_cast<uint2*>(a.y + off) = pack4(f); })
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdArgs a) {
-  const int tpc = a.C >> 3;
+__global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  const int tpc = a.C / BN_VEC;
   const int rgroups = BN_THREADS / tpc;
   const int cv = threadIdx.x % tpc, rg = threadIdx.x / tpc;
-  float mean[8], istd[8];
+  float mean[BN_VEC], istd[BN_VEC];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { mean[i] = a.mean[cv * 8 + i]; istd[i] = a.invstd[cv * 8 + i]; }
+  for (int i = 0; i < BN_VEC; ++i) { mean[i] = a.mean[cv * BN_VEC + i]; istd[i] = a.invstd[cv * BN_VEC + i]; }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   long long r1 = r0 + a.rows_per_cta; if (r1 > a.M) r1 = a.M;
-  float acc[2][8];
+  float acc[2][BN_VEC];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
-  for (long long r = r0 + rg; r < r1; r += rgroups) {
-    const long long off = r * a.C + cv * 8;
-    float d[8], xv[8];
-    unpack8(ldg16(a.dy + off), d);
-    unpack8(ldg16(a.x + off), xv);
-    if (a.relu) {
-      float yv[8];
-      unpack8(ldg16(a.y + off), yv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.f ? d[i] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[0][i] += d[i];
-      acc[1][i] = fmaf(d[i], (xv[i] - mean[i]) * istd[i], acc[1][i]);
-    }
-  }
-  cta_fold<2>(acc, a.partial + (long long)blockIdx.x * 2 * a.C, a.C, tpc, rgroups, rg, cv, bn_smem);
+  for (int i = 0; i < BN_VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  uint2 dv[BN_UNROLL], xv[BN_UNROLL], yv[BN_UNROLL];
+  const bool relu = a.relu != 0;
+  BN_ROW_LOOP(
+      { dv[u] = ldg8(a.dy + off); xv[u] = ldg8(a.x + off); if (relu) yv[u] = ldg8(a.y + off); },
+      { float d[BN_VEC]; float xf[BN_VEC]; unpack4(dv[u], d); unpack4(xv[u], xf);
+        if (relu) { float yf[BN_VEC]; unpack4(yv[u], yf); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+        _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) { acc[0][i] += d[i]; acc[1][i] = fmaf(d[i], (xf[i] - mean[i]) * istd[i], acc[1][i]); } (void)off; })
+  cta_fold(acc, a.partial + (long long)blockIdx.x * 2 * a.C, a.C, rgroups, rg, cv);
   if (last_cta(a.counter)) {
+    grid_fold(a.partial, a.C);
     const float inv_m = 1.0f / (float)a.M;
     for (int c = threadIdx.x; c < a.C; c += BN_THREADS) {
-      const float s = fold_partials(a.partial, gridDim.x, a.C, 0, c), q = fold_partials(a.partial, gridDim.x, a.C, 1, c);
+      const float s = bn_smem[c], q = bn_smem[a.C + c];
       a.dbeta[c] = s;
       a.dgamma[c] = q;
       a.sums[c] = s * inv_m;
@@ -240,56 +272,54 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdAr
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const BnBwdArgs a) {
-  const int tpc = a.C >> 3;
+__global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  const int tpc = a.C / BN_VEC;
   const int rgroups = BN_THREADS / tpc;
   const int cv = threadIdx.x % tpc, rg = threadIdx.x / tpc;
-  float mean[8], istd[8], gs[8], m1[8], m2[8];
+  // dx = gs * (d - m1 - xhat * m2) with xhat = (x - mean) * istd   ==   A * d + B * x + Cc
+  float cA[BN_VEC], cB[BN_VEC], cC[BN_VEC];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = cv * 8 + i;
-    mean[i] = a.mean[c]; istd[i] = a.invstd[c]; gs[i] = a.gamma[c] * a.invstd[c];
-    m1[i] = a.sums[c]; m2[i] = a.sums[a.C + c];
+  for (int i = 0; i < BN_VEC; ++i) {
+    const int c = cv * BN_VEC + i;
+    const float istd = a.invstd[c], gs = a.gamma[c] * istd, m1 = a.sums[c], m2 = a.sums[a.C + c], mean = a.mean[c];
+    cA[i] = gs;
+    cB[i] = -gs * m2 * istd;
+    cC[i] = gs * (m2 * istd * mean - m1);
   }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   long long r1 = r0 + a.rows_per_cta; if (r1 > a.M) r1 = a.M;
-  for (long long r = r0 + rg; r < r1; r += rgroups) {
-    const long long off = r * a.C + cv * 8;
-    float d[8], xv[8];
-    unpack8(ldg16(a.dy + off), d);
-    unpack8(ldg16(a.x + off), xv);
-    if (a.relu) {
-      float yv[8];
-      unpack8(ldg16(a.y + off), yv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.f ? d[i] : 0.f;
-    }
-    if (a.dres) *reinterpret_cast<uint4*>(a.dres + off) = pack8(d);
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xhat = (xv[i] - mean[i]) * istd[i];
-      o[i] = gs[i] * (d[i] - m1[i] - xhat * m2[i]);
-    }
-    *reinterpret_cast<uint4*>(a.dx + off) = pack8(o);
-  }
+  uint2 dv[BN_UNROLL], xv[BN_UNROLL], yv[BN_UNROLL];
+  const bool relu = a.relu != 0;
+  BN_ROW_LOOP(
+      { dv[u] = ldg8(a.dy + off); xv[u] = ldg8(a.x + off); if (relu) yv[u] = ldg8(a.y + off); },
+      { float d[BN_VEC]; float xf[BN_VEC]; unpack4(dv[u], d); unpack4(xv[u], xf);
+        if (relu) { float yf[BN_VEC]; unpack4(yv[u], yf); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+        if (a.dres) *reinterpret_cast<uint2*>(a.dres + off) = pack4(d);
+        float o[BN_VEC];
+        _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) o[i] = fmaf(cA[i], d[i], fmaf(cB[i], xf[i], cC[i]));
+        *reinterpret_cast<uint2*>(a.dx + off) = pack4(o); })
 }
 
+bool supported(int C) { return C >= BN_VEC && C <= BN_VEC * BN_THREADS && (C & (C - 1)) == 0; }
+
 int plan_rows(long long M, int C, int num_sms, int* grid) {
-  // These tensors are small (2-17 MB for ResNet-18 at B=128): a CTA should stream >= 64 KB so that the serial fold of
-  // the per-CTA partials by the last CTA (grid * 2 * C floats) stays a small fraction of the kernel.
-  const int rgroups = BN_THREADS / (C >> 3);
-  long long by_bytes = (M * (long long)C * 2 + 65535) / 65536;
-  long long cap = 32768 / C; if (cap > 2LL * num_sms) cap = 2LL * num_sms; if (cap < 1) cap = 1;
-  long long target = by_bytes < cap ? by_bytes : cap; if (target < 1) target = 1;
+  const int rgroups = BN_THREADS / (C / BN_VEC);
+  long long by_bytes = (M * (long long)C * 2 + 131071) / 131072;           // one CTA per ~128 KB of activations
+  long long target = by_bytes < num_sms ? by_bytes : num_sms;
+  if (target < 1) target = 1;
   long long rows = (M + target - 1) / target;
-  rows = (rows + rgroups - 1) / rgroups * rgroups;               // whole row-group iterations
+  rows = (rows + rgroups - 1) / rgroups * rgroups;
   if (rows < rgroups) rows = rgroups;
   *grid = (int)((M + rows - 1) / rows);
   return (int)rows;
 }
 
-bool supported(int C) { return C >= 8 && C <= 2048 && (C & (C - 1)) == 0; }
+size_t smem_bytes(int C) {
+  // cta_fold: rgroups * 2 * C floats = BN_THREADS * BN_VEC * 2 floats (32 KB); grid_fold: 2C + parts * 2C <= 2C + BN_THREADS
+  size_t a = (size_t)BN_THREADS * BN_VEC * 2 * sizeof(float);
+  size_t b = ((size_t)2 * C + BN_THREADS + 2 * C) * sizeof(float);
+  return a > b ? a : b;
+}
 
 }  // namespace
 
@@ -311,9 +341,7 @@ extern "C" int drc_bn_fwd(const void* x, const void* res, void* y, const float* 
   a.running_mean = running_mean; a.running_var = running_var; a.mean = mean; a.invstd = invstd; a.partial = partial;
   a.counter = counter; a.M = M; a.C = C; a.eps = eps; a.momentum = momentum; a.relu = relu;
   int grid; a.rows_per_cta = plan_rows(M, C, num_sms, &grid);
-  const int rgroups = BN_THREADS / (C >> 3);
-  const size_t smem = (size_t)rgroups * 2 * C * sizeof(float);    // = 256/ (C/8) * 2 * C * 4 = 16 KB
-  bn_stats_kernel<<<grid, BN_THREADS, smem, stream>>>(a);
+  bn_stats_kernel<<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
   bn_apply_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }
@@ -327,9 +355,7 @@ extern "C" int drc_bn_bwd(const void* dy, const void* y, const void* x, const fl
   a.invstd = invstd; a.dx = (__nv_bfloat16*)dx; a.dres = (__nv_bfloat16*)dres; a.dgamma = dgamma; a.dbeta = dbeta;
   a.partial = partial; a.sums = sums; a.counter = counter; a.M = M; a.C = C; a.relu = relu;
   int grid; a.rows_per_cta = plan_rows(M, C, num_sms, &grid);
-  const int rgroups = BN_THREADS / (C >> 3);
-  const size_t smem = (size_t)rgroups * 2 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<grid, BN_THREADS, smem, stream>>>(a);
+  bn_bwd_reduce_kernel<<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
   bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }

@@ -315,6 +315,15 @@ def test_cross_stream_flag_handshake(K, dev):
     step, cnt, flags = ctrl(dev, 9)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    # CUDA loads kernels lazily and the first launch of a kernel synchronises with running work: launch every kernel
+    # involved once (tables uploaded, modules loaded) before anything spins -- exactly what the engine's two eager
+    # warm-up steps do before the step graph is captured.
+    K.set_flags([flags[7:8]], step, 0)
+    K.wait_flags([flags[7:8]], step, 0, err, timeout_s=5.0)
+    K.push_encode(L, [g32], [None], out, step_ptr=step, worker=0, done_counter=cnt[0:1], flag=flags[6:7])
+    with torch.cuda.stream(s1):
+        torch.cuda._sleep(1000)
+    out.zero_()
     torch.cuda.synchronize()
     with torch.cuda.stream(s2):                      # consumer first: spins until the producer's release
         K.wait_flags([flags[0:1]], step, 0, err, timeout_s=20.0)
