@@ -138,14 +138,16 @@ __device__ __forceinline__ void grid_fold(const float* partial, int C) {
   __syncthreads();
   if (parts > 1) {
     const int idx = threadIdx.x % n_idx, part = threadIdx.x / n_idx;
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     unsigned int b = part;
-    for (; b + parts < nblk; b += 2 * parts) {
+    for (; b + 3 * parts < nblk; b += 4 * parts) {
       s0 += __ldcg(partial + (long long)b * n_idx + idx);
       s1 += __ldcg(partial + (long long)(b + parts) * n_idx + idx);
+      s2 += __ldcg(partial + (long long)(b + 2 * parts) * n_idx + idx);
+      s3 += __ldcg(partial + (long long)(b + 3 * parts) * n_idx + idx);
     }
-    if (b < nblk) s0 += __ldcg(partial + (long long)b * n_idx + idx);
-    bn_smem[n_idx + part * n_idx + idx] = s0 + s1;
+    for (; b < nblk; b += parts) s0 += __ldcg(partial + (long long)b * n_idx + idx);
+    bn_smem[n_idx + part * n_idx + idx] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (part == 0) {
       float t = 0.f;

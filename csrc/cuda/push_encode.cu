@@ -29,6 +29,9 @@ struct PushArgs {
   unsigned long long* flag;               // peer pointer: PS-side grad_ready[worker]
   float* local_copy;                      // optional local fp32 copy of what was sent (debug / NCCL path), may be null
   int tile_begin, tile_end;               // bucket of tiles to push (tile_end == 0: up to the end of the arena)
+  // Zero-copy mode: instead of arenas, a device table [R][ntensors] of pointers to each parameter's gradient tensor
+  // exactly where autograd left it (bf16 or fp32 per TensorMeta.is_bf16).  No gather / accumulate pass exists at all.
+  const void* const* src_table;
 };
 
 // counter-based normal generator (Philox-lite: 2 rounds of a 64-bit mix, Box-Muller) keyed by (seed, step, worker, idx)
@@ -46,7 +49,21 @@ __device__ __forceinline__ float2 normal_pair(unsigned long long key, unsigned l
   return make_float2(r * c, r * s);
 }
 
-__device__ __forceinline__ float4 load_grad4(const PushArgs& a, int k, int is_bf16, long long idx) {
+__device__ __forceinline__ float4 load_grad4(const PushArgs& a, int k, int tensor, int is_bf16, long long idx, int lane_valid) {
+  if (a.src_table) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane_valid <= 0) return g;
+    const long long e = idx - a.tv.meta[tensor].offset;          // element index inside the tensor (multiple of 4)
+    const void* base = a.src_table[k * a.tv.ntensors + tensor];
+    if (is_bf16) g = bf16x4_to_f4(*reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + e));
+    else g = ld_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + e));
+    if (lane_valid < 4) {                                       // tail of the tensor: lanes past numel read allocator slack
+      if (lane_valid < 2) g.y = 0.f;
+      if (lane_valid < 3) g.z = 0.f;
+      g.w = 0.f;
+    }
+    return g;
+  }
   if (is_bf16) {
     uint2 raw = *reinterpret_cast<const uint2*>(a.g16[k] + idx);
     return bf16x4_to_f4(raw);
@@ -71,7 +88,8 @@ __global__ void __launch_bounds__(DRC_THREADS) push_encode_kernel(const __grid_c
     const long long idx = (long long)tile * DRC_TILE + threadIdx.x * 4;
     const int lane_valid = valid - (int)threadIdx.x * 4;      // elements of this thread that are real
     if (!a.cyclic) {
-      float4 g = load_grad4(a, 0, is_bf16, idx);
+      if (a.src_table && lane_valid <= 0) continue;             // padding of the slab stays zero, nothing to send
+      float4 g = load_grad4(a, 0, tensor, is_bf16, idx, lane_valid);
       if (lie) {
         if (a.attack == 1) { g.x *= a.magnitude; g.y *= a.magnitude; g.z *= a.magnitude; g.w *= a.magnitude; }
         else if (a.attack == 2) { g = make_float4(a.magnitude, a.magnitude, a.magnitude, a.magnitude); }
@@ -91,10 +109,11 @@ __global__ void __launch_bounds__(DRC_THREADS) push_encode_kernel(const __grid_c
       st_f4(reinterpret_cast<float4*>(a.dst + idx), g);
       if (a.local_copy) *reinterpret_cast<float4*>(a.local_copy + idx) = g;
     } else {
+      if (a.src_table && lane_valid <= 0) continue;
       float4 re = make_float4(0.f, 0.f, 0.f, 0.f), im = re, plain = re;
 #pragma unroll 1
       for (int k = 0; k < a.R; ++k) {
-        float4 g = load_grad4(a, k, is_bf16, idx);
+        float4 g = load_grad4(a, k, tensor, is_bf16, idx, lane_valid);
         const float cr = a.coef_re[k], ci = a.coef_im[k];
         re.x = fmaf(cr, g.x, re.x); re.y = fmaf(cr, g.y, re.y); re.z = fmaf(cr, g.z, re.z); re.w = fmaf(cr, g.w, re.w);
         im.x = fmaf(ci, g.x, im.x); im.y = fmaf(ci, g.y, im.y); im.z = fmaf(ci, g.z, im.z); im.w = fmaf(ci, g.w, im.w);

@@ -51,7 +51,7 @@ class PushArgs(C.Structure):
                 ("R", C.c_int), ("cyclic", C.c_int), ("dst", ptr), ("tv", TileView), ("adv_bitmap", ptr),
                 ("adv_len", C.c_int), ("step_ptr", ptr), ("worker", C.c_int), ("attack", C.c_int),
                 ("magnitude", C.c_float), ("seed", u64), ("done_counter", ptr), ("flag", ptr), ("local_copy", ptr),
-                ("tile_begin", C.c_int), ("tile_end", C.c_int)]
+                ("tile_begin", C.c_int), ("tile_end", C.c_int), ("src_table", ptr)]
 
 
 class OmniArgs(C.Structure):

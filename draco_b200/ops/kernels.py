@@ -55,18 +55,24 @@ def _flag_list(flags: Sequence[Addr]) -> N.FlagList:
 def push_encode(layout: ArenaLayout, g32: Sequence[Addr], g16: Sequence[Addr], dst: Addr, *, step_ptr: Addr,
                 worker: int, done_counter: Addr, flag: Addr = None, coef: Optional[Sequence[complex]] = None,
                 adv_bitmap: Addr = None, adv_len: int = 0, attack: int = 0, magnitude: float = -100.0, seed: int = 428,
-                local_copy: Addr = None, grid: Optional[int] = None, tile_range: Optional[tuple] = None) -> None:
+                local_copy: Addr = None, grid: Optional[int] = None, tile_range: Optional[tuple] = None,
+                src_table: Addr = None) -> None:
     """Fused encode + adversary + store into ``dst`` (a peer pointer) + release flag.  ``coef`` given => cyclic encode
     of ``len(coef)`` gradient streams into an interleaved complex64 slot.  ``tile_range=(t0, t1)`` pushes one bucket."""
     a = N.PushArgs()
-    R = len(g32)
+    if src_table is not None:
+        # zero-copy mode: `src_table` is a device int64 [R, ntensors] table of per-tensor gradient pointers
+        R = len(coef) if coef is not None else 1
+        a.src_table = addr(src_table)
+    else:
+        R = len(g32)
+        needs_bf16 = any(sp.is_bf16 for sp in layout.specs)
+        for k in range(R):
+            a.g32[k] = addr(g32[k])
+            a.g16[k] = addr(g16[k]) if g16 and g16[k] is not None else None
+            if needs_bf16 and not a.g16[k]:
+                raise ValueError("layout has bf16 tensors: push_encode needs the bf16 gradient arena of every stream")
     assert 1 <= R <= N.MAX_R
-    needs_bf16 = any(sp.is_bf16 for sp in layout.specs)
-    for k in range(R):
-        a.g32[k] = addr(g32[k])
-        a.g16[k] = addr(g16[k]) if g16 and g16[k] is not None else None
-        if needs_bf16 and not a.g16[k]:
-            raise ValueError("layout has bf16 tensors: push_encode needs the bf16 gradient arena of every stream")
     a.R = R
     a.cyclic = 1 if coef is not None else 0
     if coef is not None:

@@ -169,15 +169,18 @@ class FusedEngine:
                              and self.schedule.is_adversary(w, step_host))
                 push_kw = dict(step_ptr=self.step_dev, worker=w - 1, done_counter=self.counters[1:2], coef=coef,
                                adv_bitmap=self.adv_bitmap, adv_len=len(self.schedule.ranks),
-                               attack=self.attack if self.attack != 4 else 0, magnitude=cfg.attack_magnitude, seed=cfg.seed)
+                               attack=self.attack if self.attack != 4 else 0, magnitude=cfg.attack_magnitude, seed=cfg.seed,
+                               src_table=wc.ptr_dev[w] if wc.zero_copy else None)
                 if self.overlap_push and not lying_now:
                     # bucketed push on a side stream, overlapped with the rest of the backward pass
                     state = {"done": 0}
                     nb = len(wc.buckets)
 
                     def on_bucket(b, _w=w, _state=state, _g32=g32, _g16=g16, _kw=push_kw):
-                        t0, t1, _ = wc.buckets[b]
+                        t0, t1, idxs = wc.buckets[b]
                         _state["done"] += 1
+                        if wc.zero_copy:                              # pointers of this bucket's gradients -> device table
+                            wc.upload_ptrs(_w, wc.R - 1, min(idxs), max(idxs) + 1)
                         ev = torch.cuda.Event()
                         ev.record()                                   # on the backward stream (autograd thread)
                         with torch.cuda.stream(self.push_stream):
@@ -191,6 +194,16 @@ class FusedEngine:
                     n += nb
                     continue
                 wc.forward_backward(w, step_host)
+                if wc.zero_copy and not lying_now:
+                    for k in range(wc.R):
+                        if k < wc.R - 1:
+                            # earlier sub-batches: their gradient tensors were detached from the parameters
+                            if not torch.cuda.is_current_stream_capturing():
+                                host = torch.tensor([g.data_ptr() for g in wc.grad_refs[w][k]], dtype=torch.int64).pin_memory()
+                                wc._pinned_keep.append(host)
+                                wc.ptr_dev[w][k].copy_(host, non_blocking=True)
+                        else:
+                            wc.upload_ptrs(w, k, 0, L.ntensors)
                 if lying_now:
                     honest = 0
                     for h in range(1, self.P + 1):
@@ -220,6 +233,11 @@ class FusedEngine:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.kernels_per_step = self._enqueue_local_step(None)
+        if self.local_workers and self.worker.zero_copy:
+            # gradients allocated during capture live at fixed addresses of the graph's pool: publish them once
+            for w in self.local_workers:
+                self.worker.upload_all_ptrs(w)
+            torch.cuda.synchronize()
 
     def _stage(self, step: int) -> int:
         if self.local_workers and self.worker.dataset is not None:
