@@ -15,7 +15,9 @@ for s in $STAGES; do
     benchnccl) timeout -k 10 600 python bench.py --gpus 1 --steps 10 --warmup 3 --impl nccl > gpurun_out/bench1_nccl.log 2>&1; echo "benchnccl rc=$?" ;;
     gemmbench) timeout -k 10 600 python tools/bench_gemm.py --json gpurun_out/gemm_bench.json > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
     ncu_gemm) timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 6 -c 2 -f -o gpurun_out/prof_gemm python tools/bench_gemm.py --quick > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
-    ncu_step) timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"push_encode|vote_compare|aggregate_update" -s 9 -c 3 -f -o gpurun_out/prof_step python tools/prof_step.py > gpurun_out/ncu_step.log 2>&1; echo "ncu_step rc=$?" ;;
+    ncu_step) timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"push_encode|vote_compare|aggregate_update|cast_params" -s 10 -c 10 -f -o gpurun_out/prof_step python tools/prof_step.py > gpurun_out/ncu_step.log 2>&1; echo "ncu_step rc=$?" ;;
+    ncu_bn) timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"bn_stats|bn_apply|bn_bwd" -s 80 -c 8 -f -o gpurun_out/prof_bn python tools/prof_step.py > gpurun_out/ncu_bn.log 2>&1; echo "ncu_bn rc=$?" ;;
+    ncu_cyclic) timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"cyclic_project|cyclic_locate|aggregate_update|push_encode" -s 9 -c 10 -f -o gpurun_out/prof_cyclic python tools/prof_step.py cyclic > gpurun_out/ncu_cyclic.log 2>&1; echo "ncu_cyclic rc=$?" ;;
     launches) STEPS=3 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/prof_step.py > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
     worker) timeout -k 10 600 python tools/bench_worker.py > gpurun_out/bench_worker.log 2>&1; echo "worker rc=$?" ;;
     diag) timeout -k 10 120 python tools/diag_flags.py > gpurun_out/diag_flags.log 2>&1; echo "diag rc=$?" ;;

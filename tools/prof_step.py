@@ -15,7 +15,7 @@ if approach == "cyclic":
 elif approach in ("krum", "geometric_median"):
     kw = dict(approach="baseline", mode=approach, worker_fail=2, err_mode="rev_grad")
 cfg = JobConfig(network="ResNet18", dataset="Cifar10", batch_size=128, num_workers=7, max_steps=16, transport="nvl", dtype="bf16",
-                cuda_graphs=False, compress_grad="None", synthetic_size=2048, eval_freq=10 ** 9, lr=0.01, momentum=0.9, **kw)
+                cuda_graphs=False, overlap_push=os.environ.get("OVERLAP", "0") == "1", compress_grad="None", synthetic_size=2048, eval_freq=10 ** 9, lr=0.01, momentum=0.9, **kw)
 t = Trainer(cfg, rank=0, world=1, device=torch.device("cuda", 0), quiet=True)
 for _ in range(int(os.environ.get("STEPS", "4"))):
     t.train_step()
