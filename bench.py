@@ -100,7 +100,20 @@ def main() -> int:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    # clocks / throttle reasons are sampled on the busiest GPU (a worker GPU when the PS has its own) over BOTH timed regions
+    busiest = eng.place.worker_procs()[0] if world > 1 else 0
+    sampler = ClockSampler(busiest, period_ms=50) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    def mean_loss(m):
+        vals = [None] * world
+        if world > 1:
+            dist.all_gather_object(vals, m.get("loss") if m else None)
+        else:
+            vals = [m.get("loss") if m else None]
+        vals = [v for v in vals if v is not None]
+        return sum(vals) / len(vals) if vals else None
 
     # ------------------------------------------------------------------ e2e: public API, pinned H2D + D2H every step
     e2e = None
@@ -122,15 +135,13 @@ def main() -> int:
         h2d = reduce_sum(float(eng.worker.h2d_bytes if eng.local_workers else 0))
         d2h = reduce_sum(12.0 if eng.local_workers else 0.0)
         e2e = {"value": a.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "final_loss": last.get("loss")}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "final_loss": mean_loss(last)}
 
     # ------------------------------------------------------------------ value: device-timed, no host sync in the loop
     cfg.data_on_device = True
     for _ in range(a.warmup):
         trainer.train_step_async()
     barrier()
-    if sampler:
-        sampler.start()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(a.steps):
@@ -162,7 +173,10 @@ def main() -> int:
                        "adversaries_per_step": a.worker_fail, "err_mode": a.err_mode, "transport": transport,
                        "cuda_graphs": bool(cfg.cuda_graphs), "nvls_multicast": bool(getattr(eng, "mc_params", None)),
                        "l2": "per-step working set (7x44.7 MB gradient slab + activations) exceeds the 126 MB L2; no explicit flush",
-                       "images_per_s": value * a.batch_size * a.num_workers},
+                       "images_per_s": value * a.batch_size * a.num_workers,
+                       "note": ("adversaries are drawn over all workers each step like the reference (src/util.py:100-103), so "
+                                "with r=3 and 3 liars a group can be out-voted and the loss may diverge; throughput is "
+                                "unaffected. Use --worker-fail 1 for a run the code provably tolerates.")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "samples_per_s": value * a.batch_size * a.num_workers,
         }
