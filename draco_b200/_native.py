@@ -146,6 +146,10 @@ def host() -> C.CDLL:
         lib.drc_codec_decode.argtypes = [ptr, u64, ptr, u64]
         lib.drc_codec_raw_size.restype = u64
         lib.drc_codec_raw_size.argtypes = [ptr, u64]
+        lib.drc_codec_valid.restype = C.c_int
+        lib.drc_codec_valid.argtypes = [ptr, u64]
+        lib.drc_codec_itemsize_flags.restype = C.c_uint
+        lib.drc_codec_itemsize_flags.argtypes = [ptr, u64]
         lib.drc_host_geomedian.argtypes = [ptr, C.c_int, i64, i64, C.c_double, C.c_int, ptr]
         lib.drc_host_vote.argtypes = [ptr, i64, i64, ptr, C.c_int]
         lib.drc_host_krum.argtypes = [ptr, C.c_int, i64, i64, C.c_int]

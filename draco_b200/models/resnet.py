@@ -17,13 +17,15 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ..ops.conv import Conv2d
 from ..ops.linear import Linear
 from ..ops.norm import FusedBatchNorm2d
 from .split import make_split
 
 
 def _conv(cin: int, cout: int, k: int, stride: int = 1) -> nn.Conv2d:
-    return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
+    # ops.conv.Conv2d is nn.Conv2d whose 1x1 / stride-1 case runs on the tcgen05 GEMM (bottleneck conv1 / conv3)
+    return Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
 
 
 class BasicBlock(nn.Module):

@@ -1,0 +1,66 @@
+"""Convolution layer whose pointwise (1x1, stride 1) case runs on the hand-written tcgen05 GEMM.
+
+In NHWC a 1x1 convolution *is* a GEMM: ``y[N*H*W, Cout] = x[N*H*W, Cin] @ W[Cout, Cin]^T`` -- both operands K-major, no
+im2col, no layout change (weights live in the arena as ``[Cout, kH, kW, Cin]``).  The three products of the layer map onto
+``csrc/cuda/gemm_tcgen05.cu`` exactly like a Linear layer (ops/linear.py): fprop K-major x K-major, dgrad with an
+MN-major B, wgrad with MN-major A and B (K = N*H*W).  This covers two thirds of the convolutions of the bottleneck
+ResNets (50/101/152: conv1, conv3 and the stride-1 projection shortcuts).  Everything else -- 3x3, strided -- goes to
+cuDNN's implicit-GEMM kernels in deterministic mode (the TMA-im2col tcgen05 convolution is the next item of the build
+plan).  ``backend_counters`` records which path served each call.
+
+Reference counterpart: ``nn.Conv2d`` inside src/model_ops/resnet.py:14-64 / vgg.py:46-59 (PyTorch-0.3 CPU THNN).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+backend_counters = {"tcgen05": 0, "cudnn": 0}
+
+
+class _Conv1x1Fn(torch.autograd.Function):
+    """x2: [M, Cin] (NHWC rows), w2: [Cout, Cin] -> y2: [M, Cout]."""
+
+    @staticmethod
+    def forward(ctx, x2, w2, bias):
+        from . import kernels as K
+        ctx.save_for_backward(x2, w2)
+        ctx.has_bias = bias is not None
+        return K.gemm_bf16(x2, w2, bias=bias)
+
+    @staticmethod
+    def backward(ctx, dy2):
+        from . import kernels as K
+        x2, w2 = ctx.saved_tensors
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = K.gemm_bf16(dy2, w2, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = K.gemm_bf16(dy2, x2, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
+        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+class Conv2d(nn.Conv2d):
+    """``nn.Conv2d`` (same parameters / state_dict) with the pointwise fast path described above."""
+
+    def _pointwise_ok(self, x: torch.Tensor) -> bool:
+        return (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0) and self.dilation == (1, 1)
+                and self.groups == 1 and x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
+                and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+                and self.in_channels % 8 == 0 and self.out_channels % 8 == 0 and self.in_channels >= 64 and self.out_channels >= 64
+                and os.environ.get("DRACO_CONV1X1", "tcgen05") == "tcgen05")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self._pointwise_ok(x):
+            backend_counters["cudnn"] += 1
+            return super().forward(x)
+        backend_counters["tcgen05"] += 1
+        n, c, h, w = x.shape
+        x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)                    # view: NHWC rows
+        w2 = self.weight.permute(0, 2, 3, 1).reshape(self.out_channels, c)  # view of the [Cout,1,1,Cin] arena storage
+        if not w2.is_contiguous():
+            w2 = w2.contiguous()
+        y2 = _Conv1x1Fn.apply(x2, w2, self.bias)
+        return y2.view(n, h, w, self.out_channels).permute(0, 3, 1, 2)      # channels-last [N, Cout, H, W]

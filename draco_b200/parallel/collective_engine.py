@@ -64,6 +64,7 @@ class CollectiveEngine:
             self.slots = torch.zeros(self.P, self.layout.total, dtype=wire, device=self.device)
             self.ps = TorchPS(cfg, self.layout, self.device, self.params_f32, self.groups, self.code)
         self.compress = cfg.compress and self.device.type == "cpu"
+        self.compress_gpu = cfg.compress and self.device.type == "cuda"
         self.bytes_up = 0
         self.bytes_up_raw = 0
 
@@ -127,6 +128,9 @@ class CollectiveEngine:
         if self.compress and self.nprocs > 1:
             self._exchange_compressed(step)
             return
+        if self.compress_gpu and self.nprocs > 1:
+            self._exchange_compressed_gpu(step)
+            return
         for w in range(1, self.P + 1):
             src_proc = self.place.proc_of[w]
             if self.is_ps and src_proc == 0:
@@ -141,6 +145,28 @@ class CollectiveEngine:
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
+
+    def _exchange_compressed_gpu(self, step: int) -> None:
+        """NCCL path with the device codec (csrc/cuda/codec.cu): the flat gradient is compressed on the GPU, the byte
+        stream travels (length first), and the PS decompresses it straight into the worker's slot."""
+        from ..utils.codec import compress_tensor, decompress_tensor
+        for w in range(1, self.P + 1):
+            src_proc = self.place.proc_of[w]
+            if self.is_ps and src_proc == 0:
+                self.slots[w - 1].copy_(self.sendbuf[w])
+                continue
+            if self.is_ps:
+                n = torch.zeros(1, dtype=torch.int64, device=self.device)
+                dist.recv(n, src=src_proc, group=self.group)
+                payload = torch.empty(int(n.item()), dtype=torch.uint8, device=self.device)
+                dist.recv(payload, src=src_proc, group=self.group)
+                self.slots[w - 1].copy_(decompress_tensor(payload, self.slots.dtype, (self.layout.total,)))
+            elif src_proc == self.rank:
+                s = compress_tensor(self.sendbuf[w])
+                self.bytes_up_raw += self.sendbuf[w].numel() * self.sendbuf[w].element_size()
+                self.bytes_up += s.numel()
+                dist.send(torch.tensor([s.numel()], dtype=torch.int64, device=self.device), dst=0, group=self.group)
+                dist.send(s, dst=0, group=self.group)
 
     def _exchange_compressed(self, step: int) -> None:
         """Gloo path with the lossless codec: per tensor, length header then payload (reference: blosc + isend)."""

@@ -116,3 +116,17 @@ def test_multi_process_peer_memory_matches_single_process():
                           cuda_graphs=True), 6)
     assert abs(single.engine.master_params().double().sum().item() - rec["param_sum"]) < 1e-9 * max(1.0, abs(rec["param_sum"]))
     assert rec["worker_param_sum"] == rec["param_sum"]
+
+
+def test_resnet50_bottlenecks_train_on_the_fused_path():
+    """ResNet-50 (BASELINE config 5 model): pointwise convs on the tcgen05 GEMM, fused BN, r=5 vote, graph replay."""
+    from draco_b200.ops.conv import backend_counters as conv_c
+    from draco_b200.ops.norm import backend_counters as bn_c
+    c0, b0 = conv_c["tcgen05"], bn_c["fused"]
+    kw = dict(approach="maj_vote", mode="maj_vote", group_size=5, worker_fail=2, err_mode="rev_grad", network="ResNet50",
+              dataset="Cifar10", batch_size=8, num_workers=5, dtype="bf16", synthetic_size=128, cuda_graphs=True)
+    t, losses = _run(_cfg(**kw), 4)
+    assert conv_c["tcgen05"] > c0 and bn_c["fused"] > b0
+    assert all(l == l for l in losses)
+    clean, _ = _run(_cfg(**dict(kw, worker_fail=0, err_mode="none")), 4)
+    assert torch.equal(t.engine.master_params(), clean.engine.master_params())      # 2 liars of 5 are out-voted, bitwise

@@ -96,3 +96,30 @@ def test_linear_layer_forward_backward(batch, fin, fout):
     assert _rel_err(x.grad, x32.grad) < 2e-2
     assert _rel_err(lin.weight.grad, w32.grad) < 2e-2
     assert _rel_err(lin.bias.grad, b32.grad) < 2e-2
+
+
+@pytest.mark.parametrize("n,cin,cout,hw", [(32, 64, 256, 16), (16, 256, 64, 8), (8, 512, 2048, 4), (128, 64, 64, 32)])
+def test_pointwise_conv_on_tcgen05(n, cin, cout, hw):
+    from draco_b200.ops.conv import Conv2d, backend_counters
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(cin + cout)
+    conv = Conv2d(cin, cout, kernel_size=1, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    x = torch.randn(n, cin, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    before = backend_counters["tcgen05"]
+    y = conv(x)
+    assert backend_counters["tcgen05"] == before + 1
+    assert y.shape == (n, cout, hw, hw) and y.is_contiguous(memory_format=torch.channels_last)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    x32 = x.detach().float().requires_grad_(True)
+    w32 = conv.weight.detach().float().requires_grad_(True)
+    y32 = F.conv2d(x32, w32)
+    y32.backward(gy.float())
+    assert _rel_err(y, y32) < 1.5e-2
+    assert _rel_err(x.grad, x32.grad) < 2e-2
+    assert _rel_err(conv.weight.grad, w32.grad) < 2e-2
+    # strided / 3x3 convolutions take the cuDNN path
+    c3 = Conv2d(cin, cout, kernel_size=3, padding=1, bias=False).to(dev).to(torch.bfloat16)
+    b2 = backend_counters["cudnn"]
+    c3(x.detach())
+    assert backend_counters["cudnn"] == b2 + 1
