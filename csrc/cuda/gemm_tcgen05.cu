@@ -377,7 +377,17 @@ extern "C" int drc_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   // autograd worker threads start without a bound context; the driver-API tensor-map encode needs one
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -3;
-  if (block_n == 0) block_n = (N > 64) ? 128 : (N > 32 ? 64 : (b_mn ? 64 : 32));
+  if (block_n == 0) {
+    block_n = (N > 64) ? 128 : (N > 32 ? 64 : (b_mn ? 64 : 32));
+    if (N >= 256 && N % 256 == 0) {
+      // prefer 128x256 tiles unless the coarser tiling loses more to wave quantisation than it gains
+      const long long mb = (M + BLOCK_M - 1) / BLOCK_M;
+      const long long t128 = mb * ((N + 127) / 128), t256 = mb * (N / 256);
+      const double eff128 = (double)t128 / (double)(((t128 + num_sms - 1) / num_sms) * num_sms);
+      const double eff256 = (double)t256 / (double)(((t256 + num_sms - 1) / num_sms) * num_sms);
+      if (eff256 * 1.12 >= eff128) block_n = 256;
+    }
+  }
   if (b_mn && block_n < 64) block_n = 64;
   CUtensorMap ta, tb;
   int r = make_tmap(&ta, A, M, K, lda, a_mn, BLOCK_M);
@@ -391,6 +401,9 @@ extern "C" int drc_gemm_bf16(const void* A, long long lda, int a_mn, const void*
     case 32: return dispatch_major<32>(a_mn, b_mn, ta, tb, g, num_sms, stream);
     case 64: return dispatch_major<64>(a_mn, b_mn, ta, tb, g, num_sms, stream);
     case 128: return dispatch_major<128>(a_mn, b_mn, ta, tb, g, num_sms, stream);
+    // 128x256 tiles: one UMMA reads 4 KB of A + 8 KB of B per 128 tensor cycles (96 B/clk) instead of 128 B/clk for
+    // 128x128, i.e. it is no longer pinned at the shared-memory bandwidth limit (profiles/ncu_gemm.md: 72.6 % tensor pipe)
+    case 256: return dispatch_major<256>(a_mn, b_mn, ta, tb, g, num_sms, stream);
     default: return -4;
   }
 }

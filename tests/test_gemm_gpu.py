@@ -40,7 +40,7 @@ def test_gemm_all_operand_orders(K, M, N, Kd, a_mn, b_mn):
     assert _rel_err(out16, ref) < 1.5e-2
 
 
-@pytest.mark.parametrize("block_n", [32, 64, 128])
+@pytest.mark.parametrize("block_n", [32, 64, 128, 256])
 def test_gemm_block_n_variants_bias_relu_accumulate(K, block_n):
     dev = torch.device("cuda", 0)
     torch.manual_seed(block_n)
