@@ -151,6 +151,17 @@ def main() -> int:
     clocks = sampler.stop() if sampler else None
     ms = reduce_max(s.elapsed_time(e))
     launches = reduce_sum(float(getattr(eng, "kernels_per_step", 0) * a.steps))
+    # device-side timeline (spin-wait stamps): how long workers wait for parameters / the PS waits for gradients per step
+    trace = eng.wait_trace(min(a.steps, 16)) if hasattr(eng, "wait_trace") else {}
+    traces = [None] * world
+    if world > 1:
+        dist.all_gather_object(traces, trace)
+    else:
+        traces = [trace]
+    ww = [t["worker_wait_ms"] for t in traces if t and "worker_wait_ms" in t]
+    breakdown = {"ps_wait_for_grads_ms": next((t["ps_wait_ms"] for t in traces if t and "ps_wait_ms" in t), None),
+                 "worker_wait_for_params_ms_mean": sum(ww) / len(ww) if ww else None,
+                 "worker_wait_for_params_ms_min": min(ww) if ww else None} if traces and any(traces) else None
     m = eng.read_metrics()
 
     if rank == 0:
@@ -177,7 +188,7 @@ def main() -> int:
                        "note": ("adversaries are drawn over all workers each step like the reference (src/util.py:100-103), so "
                                 "with r=3 and 3 liars a group can be out-voted and the loss may diverge; throughput is "
                                 "unaffected. Use --worker-fail 1 for a run the code provably tolerates.")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "breakdown": breakdown,
             "samples_per_s": value * a.batch_size * a.num_workers,
         }
         print(json.dumps(out), flush=True)

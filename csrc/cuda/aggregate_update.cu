@@ -140,23 +140,34 @@ struct WaitArgs {
   long long addend;               // wait until flag >= *step_ptr + addend
   unsigned long long timeout_ns;  // 0 = wait forever
   int* error;                     // device int: set to 1 + index of the first flag that timed out
+  unsigned long long* stamps;     // optional trace ring [64][2]: %globaltimer at entry / at release (the "Comm" time the
+                                  // reference prints per step, src/worker/baseline_worker.py:148-150, measured on the device)
 };
 
 __global__ void wait_flags_kernel(const __grid_constant__ WaitArgs a) {
   const int i = threadIdx.x;
-  if (i >= a.n) return;
-  const unsigned long long want = *a.step_ptr + a.addend;
+  const unsigned long long cur = *a.step_ptr;
   unsigned long long t0 = 0;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-  unsigned int backoff = 32;
-  while (ld_acquire_sys(a.flags[i]) < want) {
-    __nanosleep(backoff);
-    if (backoff < 1024) backoff <<= 1;
-    if (a.timeout_ns) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-      if (t1 - t0 > a.timeout_ns) { atomicCAS(a.error, 0, i + 1); return; }
+  if (i < a.n) {
+    const unsigned long long want = cur + a.addend;
+    unsigned int backoff = 32;
+    while (ld_acquire_sys(a.flags[i]) < want) {
+      __nanosleep(backoff);
+      if (backoff < 512) backoff <<= 1;
+      if (a.timeout_ns) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > a.timeout_ns) { atomicCAS(a.error, 0, i + 1); break; }
+      }
     }
+  }
+  __syncwarp();
+  if (a.stamps && i == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    a.stamps[(cur & 63) * 2] = t0;
+    a.stamps[(cur & 63) * 2 + 1] = t1;
   }
 }
 

@@ -82,7 +82,7 @@ class CastArgs(C.Structure):
 
 class WaitArgs(C.Structure):
     _fields_ = [("flags", ptr * MAX_WORKERS), ("n", C.c_int), ("step_ptr", ptr), ("addend", i64), ("timeout_ns", u64),
-                ("error", ptr)]
+                ("error", ptr), ("stamps", ptr)]
 
 
 class SetFlagArgs(C.Structure):

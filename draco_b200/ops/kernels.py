@@ -161,8 +161,10 @@ def cast_params(layout: ArenaLayout, src: Addr, dst: Addr) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ flags
-def wait_flags(flags: Sequence[Addr], step_ptr: Addr, addend: int, error: Addr, timeout_s: float = 30.0) -> None:
+def wait_flags(flags: Sequence[Addr], step_ptr: Addr, addend: int, error: Addr, timeout_s: float = 30.0,
+               stamps: Addr = None) -> None:
     a = N.WaitArgs()
+    a.stamps = addr(stamps)
     assert len(flags) <= N.MAX_WORKERS
     for i, f in enumerate(flags):
         a.flags[i] = addr(f)

@@ -102,6 +102,8 @@ class FusedEngine:
         self.step_dev = torch.ones(1, dtype=torch.int64, device=device)
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
         self.counters = torch.zeros(16, dtype=torch.int32, device=device)
+        self.stamps_worker = torch.zeros(64, 2, dtype=torch.int64, device=device)   # %globaltimer trace of the spin waits
+        self.stamps_ps = torch.zeros(64, 2, dtype=torch.int64, device=device)
         sched = generate_schedule(self.P, cfg.worker_fail, cfg.max_steps)
         self.schedule = sched
         use_adv = cfg.err_mode != "none" and cfg.worker_fail > 0
@@ -154,7 +156,7 @@ class FusedEngine:
         n = 0
         if self.local_workers:
             wc = self.worker
-            K.wait_flags([self.params_ready_ptr], self.step_dev, 0, self.error, cfg.spin_timeout_s); n += 1
+            K.wait_flags([self.params_ready_ptr], self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_worker); n += 1
             if wc.bf16:
                 K.cast_params(L, wc.binder.params_f32, wc.binder.params_c); n += 1
             order = list(self.local_workers)
@@ -219,7 +221,7 @@ class FusedEngine:
                     n += 1
         if self.is_ps:
             flags = [self.flagsB.data_ptr() + i * FLAG_STRIDE for i in range(self.P)]
-            K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s); n += 1
+            K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_ps); n += 1
             n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
                                       dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
         K.step_add(self.step_dev, 1); n += 1
@@ -287,6 +289,23 @@ class FusedEngine:
     def synchronize(self) -> None:
         torch.cuda.synchronize()
         self._check_error()
+
+    def wait_trace(self, last: int = 16) -> Dict[str, float]:
+        """Device-side timeline of the last ``last`` steps from the %globaltimer stamps of the spin-wait kernels:
+        how long this process's workers sat waiting for parameters (= everything that is not their own compute) and how
+        long the PS sat waiting for gradients, plus the step period.  Milliseconds, means."""
+        torch.cuda.synchronize()
+        out: Dict[str, float] = {}
+        cur = self.step - 1                                   # last completed step
+        idx = [(cur - i) & 63 for i in range(min(last, 60))][::-1]
+        for name, st, on in (("worker_wait_ms", self.stamps_worker, bool(self.local_workers)), ("ps_wait_ms", self.stamps_ps, self.is_ps)):
+            if not on:
+                continue
+            t = st.cpu()[idx].double()
+            out[name] = float((t[:, 1] - t[:, 0]).mean() / 1e6)
+            per = (t[1:, 0] - t[:-1, 0]) / 1e6
+            out[name.replace("wait", "period")] = float(per.mean()) if len(per) else float("nan")
+        return out
 
     def master_params(self) -> torch.Tensor:
         """The fp32 parameter arena of this process (the PS's is the master copy)."""
