@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cuda-graphs", action="store_true")
     ap.add_argument("--multicast", type=str, default="auto")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--no-overlap-push", action="store_true")
+    ap.add_argument("--push-ctas", type=int, default=48)
     return ap.parse_args()
 
 
@@ -76,7 +78,7 @@ def main() -> int:
                     num_workers=a.num_workers, group_size=a.group_size, worker_fail=a.worker_fail, err_mode=a.err_mode,
                     lr=0.01, momentum=0.9, max_steps=total_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
                     cuda_graphs=not a.no_cuda_graphs and a.impl == "ours", compress_grad="None", multicast=a.multicast,
-                    synthetic_size=8192, log_interval=10 ** 9)
+                    synthetic_size=8192, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas)
     trainer = Trainer(cfg, rank=rank, world=world, device=torch.device("cuda", local), quiet=True)
     eng = trainer.engine
     dev = torch.device("cuda", local)
@@ -191,7 +193,15 @@ def main() -> int:
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "breakdown": breakdown,
             "samples_per_s": value * a.batch_size * a.num_workers,
         }
-        print(json.dumps(out), flush=True)
+        def clean(o):                      # strict JSON: no NaN / Infinity literals
+            if isinstance(o, float) and (o != o or o in (float("inf"), float("-inf"))):
+                return None
+            if isinstance(o, dict):
+                return {k: clean(v) for k, v in o.items()}
+            if isinstance(o, list):
+                return [clean(v) for v in o]
+            return o
+        print(json.dumps(clean(out)), flush=True)
     trainer.close()
     if world > 1:
         dist.barrier()

@@ -187,7 +187,9 @@ class FusedEngine:
                         ev.record()                                   # on the backward stream (autograd thread)
                         with torch.cuda.stream(self.push_stream):
                             self.push_stream.wait_event(ev)
-                            K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1),
+                            # few CTAs: the transfer is NVLink/ingress-bound and must not starve the backward kernels
+                            # it overlaps with (a full-GPU grid of store-stalled CTAs would hog every SM's warp slots)
+                            K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1), grid=self.cfg.push_ctas,
                                           flag=self.grad_flag_ptr(_w) if _state["done"] == nb else None, **_kw)
 
                     wc.forward_backward(w, step_host, on_bucket=on_bucket)
