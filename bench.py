@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-overlap-push", action="store_true")
     ap.add_argument("--push-ctas", type=int, default=48)
+    ap.add_argument("--no-pipeline-ps", action="store_true")
     return ap.parse_args()
 
 
@@ -78,7 +79,8 @@ def main() -> int:
                     num_workers=a.num_workers, group_size=a.group_size, worker_fail=a.worker_fail, err_mode=a.err_mode,
                     lr=0.01, momentum=0.9, max_steps=total_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
                     cuda_graphs=not a.no_cuda_graphs and a.impl == "ours", compress_grad="None", multicast=a.multicast,
-                    synthetic_size=8192, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas)
+                    synthetic_size=8192, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas,
+                    pipeline_ps=not a.no_pipeline_ps)
     trainer = Trainer(cfg, rank=rank, world=world, device=torch.device("cuda", local), quiet=True)
     eng = trainer.engine
     dev = torch.device("cuda", local)

@@ -33,6 +33,7 @@ struct UpdateArgs {
   int ndst;
   unsigned int* done_counter;
   FlagList flags;                 // params_ready flags (peer pointers); value written = step + 1
+  int tile_begin, tile_end;       // bucket of tiles to update + broadcast (tile_end == 0: whole arena)
 };
 
 template <int MODE>
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(DRC_THREADS) aggregate_update_kernel(const __g
   const HyperParams hp = *a.hp;
   const unsigned long long step = *a.step_ptr;
   const bool first = (step == a.first_step);
-  for (int tile = blockIdx.x; tile < a.tv.ntiles; tile += gridDim.x) {
+  const int tile_end = a.tile_end > 0 ? a.tile_end : a.tv.ntiles;
+  for (int tile = a.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     const int tensor = a.tv.tile_tensor[tile];
     const long long idx = (long long)tile * DRC_TILE + threadIdx.x * 4;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -18,6 +18,8 @@ struct VoteArgs {
   int G, max_r;
   TileView tv;
   unsigned int* neq_mask;         // [G][ntensors] pair-mismatch bitmask, pair (i<j) -> bit i*max_r + j ... packed below
+  int tile_begin, tile_end;       // bucket of tiles to compare (tile_end == 0: whole arena) -- the PS decodes a bucket as
+                                  // soon as every worker has pushed it, while later buckets are still in flight
 };
 
 __device__ __forceinline__ int pair_bit(int i, int j) {   // i < j < 8  -> 0..27
@@ -26,7 +28,8 @@ __device__ __forceinline__ int pair_bit(int i, int j) {   // i < j < 8  -> 0..27
 
 __global__ void __launch_bounds__(DRC_THREADS) vote_compare_kernel(const __grid_constant__ VoteArgs a) {
   __shared__ unsigned int s_mask[DRC_MAX_WORKERS];       // one word per group (G <= 32)
-  for (int tile = blockIdx.x; tile < a.tv.ntiles; tile += gridDim.x) {
+  const int tile_end = a.tile_end > 0 ? a.tile_end : a.tv.ntiles;
+  for (int tile = a.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     int tensor;
     const int valid = tile_valid(a.tv, tile, tensor);
     if (threadIdx.x < a.G) s_mask[threadIdx.x] = 0u;
@@ -75,12 +78,16 @@ struct ResolveArgs {
   int* winner_slot;               // [G][T] winning worker slot
   int* winner_member;             // [G][T] winning member index (diagnostics), may be null
   unsigned int* clear_mask;       // same buffer as neq_mask: cleared for the next step after use
+  int t_begin, t_end;             // tensor range to resolve (t_end == 0: all)
 };
 
 __global__ void vote_resolve_kernel(const __grid_constant__ ResolveArgs a) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.G * a.T) return;
-  int g = i / a.T;
+  const int t_end = a.t_end > 0 ? a.t_end : a.T;
+  const int nt = t_end - a.t_begin;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.G * nt) return;
+  int g = j / nt;
+  const int i = g * a.T + a.t_begin + (j - g * nt);
   unsigned int mask = a.neq_mask[i];
   int cand = 0, count = 0;
   for (int k = 0; k < a.max_r; ++k) {
@@ -104,7 +111,7 @@ extern "C" int drc_vote_compare(const VoteArgs* args, int grid, cudaStream_t str
 }
 
 extern "C" int drc_vote_resolve(const ResolveArgs* args, cudaStream_t stream) {
-  int n = args->G * args->T;
+  int n = args->G * ((args->t_end > 0 ? args->t_end : args->T) - args->t_begin);
   vote_resolve_kernel<<<(n + 127) / 128, 128, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }

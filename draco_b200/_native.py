@@ -61,19 +61,20 @@ class OmniArgs(C.Structure):
 
 class VoteArgs(C.Structure):
     _fields_ = [("grad_in", ptr), ("slot_stride", i64), ("group_table", ptr), ("G", C.c_int), ("max_r", C.c_int),
-                ("tv", TileView), ("neq_mask", ptr)]
+                ("tv", TileView), ("neq_mask", ptr), ("tile_begin", C.c_int), ("tile_end", C.c_int)]
 
 
 class ResolveArgs(C.Structure):
     _fields_ = [("neq_mask", ptr), ("group_table", ptr), ("G", C.c_int), ("max_r", C.c_int), ("T", C.c_int),
-                ("winner_slot", ptr), ("winner_member", ptr), ("clear_mask", ptr)]
+                ("winner_slot", ptr), ("winner_member", ptr), ("clear_mask", ptr), ("t_begin", C.c_int), ("t_end", C.c_int)]
 
 
 class UpdateArgs(C.Structure):
     _fields_ = [("mode", C.c_int), ("grad_in", ptr), ("slot_stride", i64), ("select", ptr), ("K", C.c_int),
                 ("scale", C.c_float), ("recomb", ptr), ("tv", TileView), ("params", ptr), ("momentum", ptr),
                 ("hp", ptr), ("step_ptr", ptr), ("first_step", u64), ("grad_out", ptr), ("mc_params", ptr),
-                ("dst", ptr * MAX_DST), ("ndst", C.c_int), ("done_counter", ptr), ("flags", FlagList)]
+                ("dst", ptr * MAX_DST), ("ndst", C.c_int), ("done_counter", ptr), ("flags", FlagList),
+                ("tile_begin", C.c_int), ("tile_end", C.c_int)]
 
 
 class CastArgs(C.Structure):

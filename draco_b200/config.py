@@ -61,6 +61,7 @@ class JobConfig:
     num_classes: int = 10
     deterministic: bool = True
     overlap_push: bool = True       # ship gradient buckets while the remaining layers are still back-propagating
+    pipeline_ps: bool = True        # PS votes / applies / broadcasts a bucket as soon as every worker pushed it
     push_ctas: int = 48             # CTAs of an overlapped bucket push (NVLink-bound: a handful of SMs saturates the link)
     zero_copy_grads: bool = True    # push reads gradients where autograd left them (pointer table), no flat gather
 

@@ -110,15 +110,20 @@ def omniscient(grad_in: Addr, slot_stride: int, honest_mask: int, worker: int, m
 
 # ------------------------------------------------------------------------------------------------ vote (K3)
 def vote(layout: ArenaLayout, grad_in: Addr, slot_stride: int, group_table: torch.Tensor, neq_mask: torch.Tensor,
-         winner_slot: torch.Tensor, winner_member: Optional[torch.Tensor] = None) -> None:
+         winner_slot: torch.Tensor, winner_member: Optional[torch.Tensor] = None, tile_range: Optional[tuple] = None,
+         tensor_range: Optional[tuple] = None) -> None:
     """Exact-equality majority vote.  ``group_table``: int32 [G, max_r] worker slots (-1 padded); ``neq_mask``: zeroed
     uint32/int32 [G, T] scratch (left zeroed again on return); ``winner_slot``: int32 [G, T] out."""
     G, max_r = group_table.shape
     dev = group_table.device
-    va = N.VoteArgs(addr(grad_in), slot_stride, group_table.data_ptr(), G, max_r, layout.tile_view(dev), neq_mask.data_ptr())
-    N.check(N.cuda().drc_vote_compare(C.byref(va), stream_grid(layout), _stream()), "vote_compare")
+    t0, t1 = tile_range if tile_range is not None else (0, 0)
+    va = N.VoteArgs(addr(grad_in), slot_stride, group_table.data_ptr(), G, max_r, layout.tile_view(dev), neq_mask.data_ptr(),
+                    int(t0), int(t1))
+    ntiles = (t1 - t0) if tile_range is not None else layout.ntiles
+    N.check(N.cuda().drc_vote_compare(C.byref(va), max(1, min(ntiles, sm_count() * 8)), _stream()), "vote_compare")
+    q0, q1 = tensor_range if tensor_range is not None else (0, 0)
     ra = N.ResolveArgs(neq_mask.data_ptr(), group_table.data_ptr(), G, max_r, layout.ntensors, winner_slot.data_ptr(),
-                       addr(winner_member), neq_mask.data_ptr())
+                       addr(winner_member), neq_mask.data_ptr(), int(q0), int(q1))
     N.check(N.cuda().drc_vote_resolve(C.byref(ra), _stream()), "vote_resolve")
 
 
@@ -126,7 +131,8 @@ def vote(layout: ArenaLayout, grad_in: Addr, slot_stride: int, group_table: torc
 def aggregate_update(layout: ArenaLayout, grad_in: Addr, slot_stride: int, *, params: Addr, momentum: Addr, hp: Addr,
                      step_ptr: Addr, done_counter: Addr, K: int, scale: float, select: Addr = None,
                      recomb: Addr = None, first_step: int = 1, grad_out: Addr = None, mc_params: Addr = None,
-                     dst: Sequence[Addr] = (), flags: Sequence[Addr] = (), grid: Optional[int] = None) -> None:
+                     dst: Sequence[Addr] = (), flags: Sequence[Addr] = (), grid: Optional[int] = None,
+                     tile_range: Optional[tuple] = None) -> None:
     """Fused aggregate (select-sum or cyclic recombination) + SGD-momentum + parameter broadcast + flags."""
     a = N.UpdateArgs()
     a.mode = 1 if recomb is not None else 0
@@ -151,7 +157,11 @@ def aggregate_update(layout: ArenaLayout, grad_in: Addr, slot_stride: int, *, pa
     a.ndst = len(dst)
     a.done_counter = addr(done_counter)
     a.flags = _flag_list(flags)
-    N.check(N.cuda().drc_aggregate_update(C.byref(a), grid or stream_grid(layout), _stream()), "aggregate_update")
+    ntiles = layout.ntiles
+    if tile_range is not None:
+        a.tile_begin, a.tile_end = int(tile_range[0]), int(tile_range[1])
+        ntiles = a.tile_end - a.tile_begin
+    N.check(N.cuda().drc_aggregate_update(C.byref(a), grid or max(1, min(ntiles, sm_count() * 8)), _stream()), "aggregate_update")
 
 
 def cast_params(layout: ArenaLayout, src: Addr, dst: Addr) -> None:

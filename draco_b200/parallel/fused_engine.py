@@ -40,7 +40,8 @@ from .symm import SymmContext
 from .worker import WorkerCompute, make_model
 
 FLAG_STRIDE = 128            # bytes between flag words (one per 128-B line)
-FLAG_BYTES = 8192
+FLAG_BYTES = 65536
+MAX_BUCKETS = 8              # per-worker gradient-bucket flags
 
 
 class FusedEngine:
@@ -62,6 +63,10 @@ class FusedEngine:
         self._use_graph = cfg.cuda_graphs and cfg.err_mode != "omniscient"
         self._eager_steps = 0
         self.overlap_push = cfg.overlap_push and not self.cyclic
+        # PS pipelining: decode + apply + broadcast each gradient bucket as soon as all workers pushed it
+        from .ps import select_rule
+        self.pipeline_ps = (self.overlap_push and cfg.pipeline_ps and select_rule(cfg) in ("mean", "vote")
+                            and cfg.err_mode != "omniscient")
         self.push_stream = torch.cuda.Stream(device=device) if self.overlap_push else None
         self._staged_step = -1
 
@@ -146,8 +151,8 @@ class FusedEngine:
     def slot_ptr(self, w: int) -> int:
         return self.ps_grad_base + (w - 1) * self.layout.total * self.esize
 
-    def grad_flag_ptr(self, w: int) -> int:
-        return self.ps_flag_base + (w - 1) * FLAG_STRIDE
+    def grad_flag_ptr(self, w: int, b: int = 0) -> int:
+        return self.ps_flag_base + ((w - 1) * MAX_BUCKETS + b) * FLAG_STRIDE
 
     # ------------------------------------------------------------------ the step
     def _enqueue_local_step(self, step_host: Optional[int]) -> int:
@@ -189,8 +194,12 @@ class FusedEngine:
                             self.push_stream.wait_event(ev)
                             # few CTAs: the transfer is NVLink/ingress-bound and must not starve the backward kernels
                             # it overlaps with (a full-GPU grid of store-stalled CTAs would hog every SM's warp slots)
+                            if self.pipeline_ps:
+                                flag = self.grad_flag_ptr(_w, b)                  # every bucket announces itself
+                            else:
+                                flag = self.grad_flag_ptr(_w) if _state["done"] == nb else None
                             K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1), grid=self.cfg.push_ctas,
-                                          flag=self.grad_flag_ptr(_w) if _state["done"] == nb else None, **_kw)
+                                          flag=flag, **_kw)
 
                     wc.forward_backward(w, step_host, on_bucket=on_bucket)
                     assert state["done"] == nb, "a gradient bucket never became ready"
@@ -222,10 +231,22 @@ class FusedEngine:
                     K.push_encode(L, g32, g16, self.slot_ptr(w), flag=self.grad_flag_ptr(w), **push_kw)
                     n += 1
         if self.is_ps:
-            flags = [self.flagsB.data_ptr() + i * FLAG_STRIDE for i in range(self.P)]
-            K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_ps); n += 1
-            n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
-                                      dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
+            base = self.flagsB.data_ptr()
+            if self.pipeline_ps:
+                nb = len(self.worker.buckets)
+
+                def wait_bucket(bi):
+                    fl = [base + (i * MAX_BUCKETS + bi) * FLAG_STRIDE for i in range(self.P)]
+                    K.wait_flags(fl, self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_ps if bi == nb - 1 else None)
+                    return 1
+
+                n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params, dst=[] if self.mc_params else self.dst_ptrs,
+                                          flags=self.param_flag_ptrs, buckets=self.worker.buckets, wait_bucket=wait_bucket)
+            else:
+                flags = [base + i * MAX_BUCKETS * FLAG_STRIDE for i in range(self.P)]
+                K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_ps); n += 1
+                n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
+                                          dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
         K.step_add(self.step_dev, 1); n += 1
         return n
 

@@ -82,13 +82,31 @@ class FusedPS:
             self.f = f.to(device)
 
     def enqueue_step(self, step_ptr: torch.Tensor, *, mc_params: Optional[int], dst: Sequence[int], flags: Sequence[int],
-                     grad_out: Optional[torch.Tensor] = None) -> int:
-        """Decode + update + broadcast for the step in ``*step_ptr``.  Returns the number of kernels launched."""
+                     grad_out: Optional[torch.Tensor] = None, buckets=None, wait_bucket=None) -> int:
+        """Decode + update + broadcast for the step in ``*step_ptr``.  Returns the number of kernels launched.
+
+        With ``buckets`` (the workers' push buckets, in arrival order) and ``wait_bucket(b)`` the PS is pipelined: bucket
+        ``b`` is voted on, applied and broadcast as soon as every worker has pushed it, while the workers are still
+        back-propagating / pushing the later buckets; only the last bucket is on the critical path."""
         K, L = self.K, self.layout
         common = dict(params=self.params, momentum=self.momentum, hp=self.hp, step_ptr=step_ptr,
-                      done_counter=self.counters[0:1], first_step=1, grad_out=grad_out, mc_params=mc_params, dst=dst,
-                      flags=flags)
+                      done_counter=self.counters[0:1], first_step=1, grad_out=grad_out, mc_params=mc_params, dst=dst)
         n = 0
+        if buckets is not None and self.rule in ("mean", "vote"):
+            for bi, (t0, t1, idxs) in enumerate(buckets):
+                n += wait_bucket(bi)
+                fl = flags if bi == len(buckets) - 1 else []
+                if self.rule == "vote":
+                    K.vote(L, self.grad_in, self.slot_stride, self.group_table, self.neq_mask, self.winner_slot,
+                           self.winner_member, tile_range=(t0, t1), tensor_range=(min(idxs), max(idxs) + 1)); n += 2
+                    G = self.group_table.shape[0]
+                    K.aggregate_update(L, self.grad_in, self.slot_stride, K=G, scale=1.0 / G, select=self.winner_slot,
+                                       tile_range=(t0, t1), flags=fl, **common); n += 1
+                else:
+                    K.aggregate_update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0 / self.P,
+                                       tile_range=(t0, t1), flags=fl, **common); n += 1
+            return n
+        common["flags"] = flags
         if self.rule == "mean":
             K.aggregate_update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0 / self.P, **common); n += 1
         elif self.rule == "vote":
