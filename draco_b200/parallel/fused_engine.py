@@ -198,7 +198,9 @@ class FusedEngine:
                                 flag = self.grad_flag_ptr(_w, b)                  # every bucket announces itself
                             else:
                                 flag = self.grad_flag_ptr(_w) if _state["done"] == nb else None
-                            K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1), grid=self.cfg.push_ctas,
+                            # remote slot: NVLink-bound, few CTAs; local slot (PS on this GPU): HBM-bound, 2 CTAs per SM
+                            grid = self.cfg.push_ctas if self.rank != 0 else 2 * K.sm_count()
+                            K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1), grid=min(grid, t1 - t0),
                                           flag=flag, **_kw)
 
                     wc.forward_backward(w, step_host, on_bucket=on_bucket)
