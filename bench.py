@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--multicast", type=str, default="auto")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-overlap-push", action="store_true")
-    ap.add_argument("--push-ctas", type=int, default=48)
+    ap.add_argument("--push-ctas", type=int, default=16)
     ap.add_argument("--no-pipeline-ps", action="store_true")
     return ap.parse_args()
 

@@ -62,7 +62,7 @@ class JobConfig:
     deterministic: bool = True
     overlap_push: bool = True       # ship gradient buckets while the remaining layers are still back-propagating
     pipeline_ps: bool = True        # PS votes / applies / broadcasts a bucket as soon as every worker pushed it
-    push_ctas: int = 48             # CTAs of an overlapped bucket push (NVLink-bound: a handful of SMs saturates the link)
+    push_ctas: int = 16             # CTAs of an overlapped bucket push (NVLink-bound: a handful of SMs saturates the link)
     zero_copy_grads: bool = True    # push reads gradients where autograd left them (pointer table), no flat gather
 
     # ---- derived --------------------------------------------------------------------------

@@ -32,22 +32,27 @@ def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1, 5)) -> List[to
     return [correct[:min(k, maxk)].reshape(-1).float().sum() * (100.0 / target.shape[0]) for k in topk]
 
 
-def plan_buckets(layout: ArenaLayout, nbuckets: int = 4):
-    """Split the arena into ``<= nbuckets`` contiguous tile ranges of similar size, returned in the order backprop
-    finishes them (last layers first): ``[(tile_begin, tile_end, [param indices]), ...]``."""
+def plan_buckets(layout: ArenaLayout, nbuckets: int = 5):
+    """Split the arena into contiguous tile ranges (whole tensors), returned in the order backprop finishes them (last
+    layers first): ``[(tile_begin, tile_end, [param indices]), ...]``.  Cut points are at growing fractions of the bytes
+    (35 / 65 / 85 / 95 % for 5 buckets): the early buckets are large (their transfer hides behind the rest of backprop),
+    the final bucket -- the only one whose push is exposed after backprop ends -- is ~5 % of the model."""
     from .arena import TILE
     total = layout.ntiles
-    target = max(total // max(nbuckets, 1), 1)
-    buckets, cur, cur_tiles = [], [], 0
+    fracs = {1: [], 2: [0.75], 3: [0.5, 0.9], 4: [0.4, 0.75, 0.95]}.get(nbuckets, [0.35, 0.65, 0.85, 0.95])
+    cuts = [int(f * total) for f in fracs]
+    buckets, cur, done_tiles = [], [], 0
     end_tile = total
     for i in range(layout.ntensors - 1, -1, -1):
         s = layout.specs[i]
         cur.append(i)
-        cur_tiles += (s.numel + TILE - 1) // TILE
-        if cur_tiles >= target and len(buckets) < nbuckets - 1 and i > 0:
+        done_tiles += (s.numel + TILE - 1) // TILE
+        if cuts and done_tiles >= cuts[0] and i > 0:
             begin = s.offset // TILE
             buckets.append((begin, end_tile, cur))
-            end_tile, cur, cur_tiles = begin, [], 0
+            end_tile, cur = begin, []
+            while cuts and done_tiles >= cuts[0]:
+                cuts.pop(0)
     if cur:
         buckets.append((0, end_tile, cur))
     return buckets
@@ -89,7 +94,7 @@ class WorkerCompute:
                 self.grad_refs[wk] = [None] * self.R
         # gradient buckets (contiguous tile ranges, listed in the order backprop completes them) + readiness hooks:
         # the transport can ship a bucket while the remaining layers are still back-propagating
-        self.buckets = plan_buckets(self.layout, 4)
+        self.buckets = plan_buckets(self.layout, 5)
         self._param_bucket = {i: b for b, (_, _, idxs) in enumerate(self.buckets) for i in idxs}
         self._bucket_left: List[int] = []
         self._bucket_cb = None
