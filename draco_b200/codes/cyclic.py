@@ -162,3 +162,40 @@ def decode(code: CyclicCode, R: np.ndarray, f: Optional[np.ndarray] = None,
 def encode(code: CyclicCode, worker: int, grads_by_batch: np.ndarray) -> np.ndarray:
     """Oracle encode: ``grads_by_batch`` is [n, d] (all batches); returns worker's complex row [d]."""
     return code.W[worker, :] @ np.asarray(grads_by_batch, dtype=np.complex128)
+
+
+def decode_ifft(code: CyclicCode, R: np.ndarray, f: Optional[np.ndarray] = None) -> np.ndarray:
+    """Alternative decoder: estimate the error matrix and subtract it (the reference's earlier, now dead, decoder --
+    ``_obtain_E`` / ``_obtain_epsilon`` in src/master/cyclic_master.py:175-188 and the orphan Cython ``decoding`` module,
+    SURVEY N3).
+
+    The syndrome ``C2^H R`` holds the last 2s DFT coefficients of every error column.  The locator polynomial (from the
+    projected syndrome, as in :func:`decode`) gives a linear recurrence that extends them cyclically to all n
+    coefficients; an inverse DFT then yields the error matrix ``eps`` itself, and ``S (R - eps) = sum_j g_j``.
+    Cost: O(n d) like the recombination decoder, but it also *returns what every liar added*."""
+    n, s = code.n, code.s
+    R = np.asarray(R, dtype=np.complex128)
+    d = R.shape[1]
+    if f is None:
+        f = np.ones(d)
+    if s == 0:
+        return np.real((code.S @ R)[0])
+    k = n - 2 * s
+    synd_full = code.W_perp @ R                                   # [2s, d] : spectrum indices k .. n-1
+    proj = synd_full @ f
+    A, b = hankel_system(proj, s)
+    if np.abs(proj).max() <= 1e-7 * max(np.abs(R @ f).max(), 1e-300):
+        eps = np.zeros_like(R)
+    else:
+        alpha = np.linalg.lstsq(A, b, rcond=1e-10)[0]
+        spec = np.zeros((n + k, d), dtype=np.complex128)          # spectrum laid out k .. n-1, then n .. n+k-1 (== 0 .. k-1)
+        spec[: 2 * s] = synd_full
+        for t in range(2 * s, 2 * s + k):                         # E[t] = sum_j alpha_j E[t - s + j]
+            spec[t] = sum(alpha[j] * spec[t - s + j] for j in range(s))
+        full = np.zeros((n, d), dtype=np.complex128)
+        full[k:] = spec[: 2 * s]
+        full[:k] = spec[2 * s: 2 * s + k]
+        C = dft_matrix(n)
+        eps = C @ full                                            # eps = C * (C^H eps)
+    clean = R - eps
+    return np.real((code.S @ clean)[0])

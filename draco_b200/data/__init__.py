@@ -54,6 +54,24 @@ class TensorDataset:
         idx = torch.as_tensor(np.asarray(indices), dtype=torch.long)
         return self.images[idx], self.labels[idx]
 
+    def next_batch(self, batch_size: int, shuffle: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Sequential mini-batches with an epoch counter -- the reference's legacy ``MNISTDataset.next_batch`` /
+        ``DataLoader.next_batch`` API (src/datasets/__init__.py:5-51, src/data_loader_ops/my_data_loader.py:254-319)."""
+        st = self.__dict__.setdefault("_nb_state", {"pos": 0, "perm": None, "epochs_completed": 0})
+        n = len(self)
+        if st["perm"] is None or st["pos"] + batch_size > n:
+            if st["perm"] is not None:
+                st["epochs_completed"] += 1
+            st["perm"] = torch.randperm(n) if shuffle else torch.arange(n)
+            st["pos"] = 0
+        idx = st["perm"][st["pos"]: st["pos"] + batch_size]
+        st["pos"] += batch_size
+        return self.normalize(self.images[idx]), self.labels[idx]
+
+    @property
+    def epochs_completed(self) -> int:
+        return self.__dict__.get("_nb_state", {}).get("epochs_completed", 0)
+
     def normalize(self, x_u8: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
         x = x_u8.to(torch.float32) / 255.0
         return ((x - self.mean.to(x.device)) / self.std.to(x.device)).to(dtype)

@@ -38,6 +38,21 @@ def test_cyclic_decode_recovers_sum_for_every_adversary_subset(n, s):
             assert np.abs(dec - G.sum(0)).max() < 1e-6 * max(1.0, np.abs(G.sum(0)).max())
 
 
+@pytest.mark.parametrize("n,s,liars", [(7, 2, (1, 4)), (7, 3, (0, 2, 6)), (7, 2, ()), (5, 1, (3,)), (9, 2, (8,)), (7, 2, (5,))])
+def test_ifft_decoder_agrees_and_exposes_the_error(n, s, liars):
+    """The alternative 'estimate eps and subtract' decoder (reference's dead `_obtain_E` path / orphan decoding.o)."""
+    rng = np.random.RandomState(5)
+    c = cyclic.search_w(n, s)
+    G = rng.randn(n, 24)
+    f = rng.randn(24) + 1.0
+    R = np.stack([cyclic.encode(c, i, G) for i in range(n)])
+    for l in liars:
+        R[l] += -100.0 * (1 + rng.rand(24))
+    d1, _ = cyclic.decode(c, R, f)
+    d2 = cyclic.decode_ifft(c, R, f)
+    assert np.abs(d1 - G.sum(0)).max() < 1e-8 and np.abs(d2 - G.sum(0)).max() < 1e-8
+
+
 def test_cyclic_decode_fails_beyond_tolerance():
     rng = np.random.RandomState(1)
     c = cyclic.search_w(7, 1)
