@@ -302,6 +302,131 @@ __global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_apply_kernel(const BnBwd
         *reinterpret_cast<uint2*>(a.dx + off) = pack4(o); })
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cooperative single-kernel variants: pass 1 (statistics / gradient sums), a grid-wide barrier, then pass 2 (apply) over
+// the SAME rows by the same CTA -- the second read of x (dy, y) is an L2 hit, one launch and one reduction tail are gone.
+// Launched with cudaLaunchCooperativeKernel (grid <= #SMs, one 1024-thread CTA per SM) so that all CTAs are co-resident
+// and the barrier cannot deadlock even while push kernels of the side stream share the SMs.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* bar) {
+  __threadfence();                                 // every thread publishes its partial sums before the CTA arrives
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&bar[0], 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(&bar[0]) < gridDim.x) { __nanosleep(32); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void grid_barrier_release(unsigned int* bar) {       // at kernel end: reset for the next launch
+  if (threadIdx.x == 0) {
+    unsigned int prev = atomicAdd(&bar[1], 1u);
+    if (prev == gridDim.x - 1) { bar[0] = 0; bar[1] = 0; __threadfence(); }
+  }
+}
+
+__global__ void __launch_bounds__(BN_THREADS, 1) bn_fwd_coop_kernel(const BnFwdArgs a) {
+  const int tpc = a.C / BN_VEC;
+  const int rgroups = BN_THREADS / tpc;
+  const int cv = threadIdx.x % tpc, rg = threadIdx.x / tpc;
+  const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
+  long long r1 = r0 + a.rows_per_cta; if (r1 > a.M) r1 = a.M;
+  {
+    float acc[2][BN_VEC];
+#pragma unroll
+    for (int i = 0; i < BN_VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+    uint2 xv[BN_UNROLL];
+    BN_ROW_LOOP(
+        { xv[u] = ldg8(a.x + off); },
+        { float f[BN_VEC]; unpack4(xv[u], f);
+          _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) { acc[0][i] += f[i]; acc[1][i] = fmaf(f[i], f[i], acc[1][i]); } (void)off; })
+    cta_fold(acc, a.partial + (long long)blockIdx.x * 2 * a.C, a.C, rgroups, rg, cv);
+  }
+  grid_barrier(a.counter + 2);
+  grid_fold(a.partial, a.C);                       // every CTA folds the same partials in the same order
+  const float inv_m = 1.0f / (float)a.M;
+  float scale[BN_VEC], shift[BN_VEC];
+#pragma unroll
+  for (int i = 0; i < BN_VEC; ++i) {
+    const int c = cv * BN_VEC + i;
+    const float m = bn_smem[c] * inv_m;
+    float var = fmaf(-m, m, bn_smem[a.C + c] * inv_m);
+    var = var < 0.f ? 0.f : var;
+    const float istd = rsqrtf(var + a.eps);
+    const float sc = a.gamma[c] * istd;
+    scale[i] = sc;
+    shift[i] = fmaf(-m, sc, a.beta[c]);
+    if (blockIdx.x == 0 && rg == 0) {
+      a.mean[c] = m;
+      a.invstd[c] = istd;
+      if (a.running_mean) {
+        const float unbiased = a.M > 1 ? var * ((float)a.M / (float)(a.M - 1)) : var;
+        a.running_mean[c] = fmaf(a.momentum, m - a.running_mean[c], a.running_mean[c]);
+        a.running_var[c] = fmaf(a.momentum, unbiased - a.running_var[c], a.running_var[c]);
+      }
+    }
+  }
+  uint2 xv[BN_UNROLL], rv[BN_UNROLL];
+  const bool has_res = a.res != nullptr;
+  BN_ROW_LOOP(
+      { xv[u] = ldg8(a.x + off); if (has_res) rv[u] = ldg8(a.res + off); },
+      { float f[BN_VEC]; unpack4(xv[u], f);
+        _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
+        if (has_res) { float g[BN_VEC]; unpack4(rv[u], g); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) f[i] += g[i]; }
+        if (a.relu) { _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) f[i] = fmaxf(f[i], 0.f); }
+        *reinterpret_cast<uint2*>(a.y + off) = pack4(f); })
+  grid_barrier_release(a.counter + 2);
+}
+
+__global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_coop_kernel(const BnBwdArgs a) {
+  const int tpc = a.C / BN_VEC;
+  const int rgroups = BN_THREADS / tpc;
+  const int cv = threadIdx.x % tpc, rg = threadIdx.x / tpc;
+  float mean[BN_VEC], istd[BN_VEC];
+#pragma unroll
+  for (int i = 0; i < BN_VEC; ++i) { mean[i] = a.mean[cv * BN_VEC + i]; istd[i] = a.invstd[cv * BN_VEC + i]; }
+  const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
+  long long r1 = r0 + a.rows_per_cta; if (r1 > a.M) r1 = a.M;
+  const bool relu = a.relu != 0;
+  {
+    float acc[2][BN_VEC];
+#pragma unroll
+    for (int i = 0; i < BN_VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+    uint2 dv[BN_UNROLL], xv[BN_UNROLL], yv[BN_UNROLL];
+    BN_ROW_LOOP(
+        { dv[u] = ldg8(a.dy + off); xv[u] = ldg8(a.x + off); if (relu) yv[u] = ldg8(a.y + off); },
+        { float d[BN_VEC]; float xf[BN_VEC]; unpack4(dv[u], d); unpack4(xv[u], xf);
+          if (relu) { float yf[BN_VEC]; unpack4(yv[u], yf); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+          _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) { acc[0][i] += d[i]; acc[1][i] = fmaf(d[i], (xf[i] - mean[i]) * istd[i], acc[1][i]); } (void)off; })
+    cta_fold(acc, a.partial + (long long)blockIdx.x * 2 * a.C, a.C, rgroups, rg, cv);
+  }
+  grid_barrier(a.counter + 2);
+  grid_fold(a.partial, a.C);
+  const float inv_m = 1.0f / (float)a.M;
+  float cA[BN_VEC], cB[BN_VEC], cC[BN_VEC];
+#pragma unroll
+  for (int i = 0; i < BN_VEC; ++i) {
+    const int c = cv * BN_VEC + i;
+    const float s = bn_smem[c], q = bn_smem[a.C + c];
+    if (blockIdx.x == 0 && rg == 0) { a.dbeta[c] = s; a.dgamma[c] = q; }
+    const float gs = a.gamma[c] * istd[i], m1 = s * inv_m, m2 = q * inv_m;
+    cA[i] = gs;
+    cB[i] = -gs * m2 * istd[i];
+    cC[i] = gs * (m2 * istd[i] * mean[i] - m1);
+  }
+  uint2 dv[BN_UNROLL], xv[BN_UNROLL], yv[BN_UNROLL];
+  BN_ROW_LOOP(
+      { dv[u] = ldg8(a.dy + off); xv[u] = ldg8(a.x + off); if (relu) yv[u] = ldg8(a.y + off); },
+      { float d[BN_VEC]; float xf[BN_VEC]; unpack4(dv[u], d); unpack4(xv[u], xf);
+        if (relu) { float yf[BN_VEC]; unpack4(yv[u], yf); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+        if (a.dres) *reinterpret_cast<uint2*>(a.dres + off) = pack4(d);
+        float o[BN_VEC];
+        _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) o[i] = fmaf(cA[i], d[i], fmaf(cB[i], xf[i], cC[i]));
+        *reinterpret_cast<uint2*>(a.dx + off) = pack4(o); })
+  grid_barrier_release(a.counter + 2);
+}
+
 bool supported(int C) { return C >= BN_VEC && C <= BN_VEC * BN_THREADS && (C & (C - 1)) == 0; }
 
 int plan_rows(long long M, int C, int num_sms, int* grid) {
@@ -336,13 +461,17 @@ extern "C" long long drc_bn_workspace(long long M, int C, int num_sms) {
 
 extern "C" int drc_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float* mean, float* invstd, float* partial, unsigned int* counter, long long M, int C,
-                          float eps, float momentum, int relu, int num_sms, cudaStream_t stream) {
+                          float eps, float momentum, int relu, int num_sms, int coop, cudaStream_t stream) {
   if (!supported(C)) return -1;
   BnFwdArgs a;
   a.x = (const __nv_bfloat16*)x; a.res = (const __nv_bfloat16*)res; a.y = (__nv_bfloat16*)y; a.gamma = gamma; a.beta = beta;
   a.running_mean = running_mean; a.running_var = running_var; a.mean = mean; a.invstd = invstd; a.partial = partial;
   a.counter = counter; a.M = M; a.C = C; a.eps = eps; a.momentum = momentum; a.relu = relu;
   int grid; a.rows_per_cta = plan_rows(M, C, num_sms, &grid);
+  if (coop) {
+    void* kargs[] = {&a};
+    return (int)cudaLaunchCooperativeKernel((const void*)bn_fwd_coop_kernel, dim3(grid), dim3(BN_THREADS), kargs, smem_bytes(C), stream);
+  }
   bn_stats_kernel<<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
   bn_apply_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
   return (int)cudaGetLastError();
@@ -350,13 +479,17 @@ extern "C" int drc_bn_fwd(const void* x, const void* res, void* y, const float* 
 
 extern "C" int drc_bn_bwd(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* invstd,
                           void* dx, void* dres, float* dgamma, float* dbeta, float* partial, float* sums, unsigned int* counter,
-                          long long M, int C, int relu, int num_sms, cudaStream_t stream) {
+                          long long M, int C, int relu, int num_sms, int coop, cudaStream_t stream) {
   if (!supported(C)) return -1;
   BnBwdArgs a;
   a.dy = (const __nv_bfloat16*)dy; a.y = (const __nv_bfloat16*)y; a.x = (const __nv_bfloat16*)x; a.gamma = gamma; a.mean = mean;
   a.invstd = invstd; a.dx = (__nv_bfloat16*)dx; a.dres = (__nv_bfloat16*)dres; a.dgamma = dgamma; a.dbeta = dbeta;
   a.partial = partial; a.sums = sums; a.counter = counter; a.M = M; a.C = C; a.relu = relu;
   int grid; a.rows_per_cta = plan_rows(M, C, num_sms, &grid);
+  if (coop) {
+    void* kargs[] = {&a};
+    return (int)cudaLaunchCooperativeKernel((const void*)bn_bwd_coop_kernel, dim3(grid), dim3(BN_THREADS), kargs, smem_bytes(C), stream);
+  }
   bn_bwd_reduce_kernel<<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
   bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
   return (int)cudaGetLastError();

@@ -31,9 +31,9 @@ def _lib():
         lib.drc_bn_supported.restype = C.c_int
         lib.drc_bn_workspace.argtypes = [N.i64, C.c_int, C.c_int]
         lib.drc_bn_workspace.restype = N.i64
-        lib.drc_bn_fwd.argtypes = [N.ptr] * 11 + [N.i64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, st]
+        lib.drc_bn_fwd.argtypes = [N.ptr] * 11 + [N.i64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, st]
         lib.drc_bn_fwd.restype = C.c_int
-        lib.drc_bn_bwd.argtypes = [N.ptr] * 13 + [N.i64, C.c_int, C.c_int, C.c_int, st]
+        lib.drc_bn_bwd.argtypes = [N.ptr] * 13 + [N.i64, C.c_int, C.c_int, C.c_int, C.c_int, st]
         lib.drc_bn_bwd.restype = C.c_int
         lib._bn_ready = True
     return lib
@@ -41,8 +41,13 @@ def _lib():
 
 def _counter(device: torch.device) -> torch.Tensor:
     if device not in _counter_cache:
-        _counter_cache[device] = torch.zeros(4, dtype=torch.int32, device=device)
+        _counter_cache[device] = torch.zeros(16, dtype=torch.int32, device=device)
     return _counter_cache[device]
+
+
+def _coop() -> int:
+    """1: single cooperative kernel per direction (statistics, grid barrier, apply); 0: two kernels."""
+    return 0 if os.environ.get("DRACO_BN_COOP", "1") == "0" else 1
 
 
 def _sms(device: torch.device) -> int:
@@ -74,7 +79,7 @@ class _BnActFn(torch.autograd.Function):
             residual = residual.contiguous(memory_format=torch.channels_last)
         N.check(lib.drc_bn_fwd(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
                                _p(running_var), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), _counter(dev).data_ptr(),
-                               M, c, float(eps), float(momentum), int(relu), _sms(dev),
+                               M, c, float(eps), float(momentum), int(relu), _sms(dev), _coop(),
                                torch.cuda.current_stream().cuda_stream), "bn_fwd")
         ctx.save_for_backward(x, y if relu else None, gamma, mean, invstd)
         ctx.relu, ctx.has_res = bool(relu), residual is not None
@@ -98,7 +103,7 @@ class _BnActFn(torch.autograd.Function):
         torch.cuda.set_device(dev)
         N.check(lib.drc_bn_bwd(dy.data_ptr(), _p(y), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                dx.data_ptr(), _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), sums.data_ptr(),
-                               _counter(dev)[1:].data_ptr(), M, c, int(ctx.relu), _sms(dev),
+                               _counter(dev)[8:].data_ptr(), M, c, int(ctx.relu), _sms(dev), _coop(),
                                torch.cuda.current_stream().cuda_stream), "bn_bwd")
         return dx, dres, dgamma, dbeta, None, None, None, None, None
 

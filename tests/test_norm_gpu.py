@@ -21,7 +21,10 @@ def _ref(x, res, gamma, beta, relu, eps=1e-5):
 
 @pytest.mark.parametrize("shape", [(128, 64, 32, 32), (32, 128, 16, 16), (16, 256, 8, 8), (128, 512, 4, 4), (3, 8, 5, 7), (2, 2048, 4, 4)])
 @pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False), (False, True)])
-def test_fused_bn_matches_fp32_reference(shape, relu, with_res):
+@pytest.mark.parametrize("coop", ["1", "0"])
+def test_fused_bn_matches_fp32_reference(shape, relu, with_res, coop, monkeypatch):
+    """coop=1: one cooperative kernel per direction (grid barrier between statistics and apply); coop=0: two kernels."""
+    monkeypatch.setenv("DRACO_BN_COOP", coop)
     from draco_b200.ops.norm import FusedBatchNorm2d, backend_counters
     dev = torch.device("cuda", 0)
     torch.manual_seed(sum(shape))
