@@ -1,0 +1,65 @@
+"""CPU tests: cluster tool, bucket planning, op fallbacks (Conv2d / FusedBatchNorm2d / Linear on CPU are plain ATen)."""
+import json
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from draco_b200.cli import cluster
+from draco_b200.models import build_model
+from draco_b200.ops.conv import Conv2d
+from draco_b200.ops.linear import Linear
+from draco_b200.ops.norm import FusedBatchNorm2d
+from draco_b200.parallel.arena import ArenaLayout
+from draco_b200.parallel.worker import plan_buckets
+
+
+def test_cfg_self_interpolation_and_hosts(tmp_path):
+    cfg = cluster.Cfg({"name": "job", "ssh_user": "me", "remote_dir": "/home/%(ssh_user)s/%(name)s",
+                       "train_dir": "%(remote_dir)s/models/", "nodes": ["10.0.0.1", "10.0.0.2"]})
+    assert cfg["remote_dir"] == "/home/me/job" and cfg["train_dir"] == "/home/me/job/models/"
+    files = cluster.get_hosts(cfg, str(tmp_path))
+    assert files["hosts_address"] == "10.0.0.1\n10.0.0.2\n" and "node1" in files["hosts"]
+    assert (tmp_path / "hosts_alias").read_text().split() == ["node0", "node1"]
+    full = cluster.load_cfg(None)
+    cmd = cluster.job_command(full, ["--network", "ResNet18", "--approach", "cyclic"], node_rank=0, nnodes=1, nproc=8)
+    assert "torch.distributed.run" in cmd and "--nproc-per-node=8" in cmd and "draco_b200.cli.distributed_nn" in cmd
+    # local "cluster": check + idle work without ssh
+    local = cluster.Cfg(dict(cluster.DEFAULT_CFG, nodes=["127.0.0.1"], state_file=str(tmp_path / "state.json")))
+    assert cluster.check(local)["127.0.0.1"]["reachable"] in (True, False)
+    assert cluster.idle(local) == {"127.0.0.1": True}
+
+
+def test_bucket_plan_covers_arena_in_backprop_order():
+    for name in ("LeNet", "ResNet18", "VGG11", "ResNet50"):
+        L = ArenaLayout.from_model(build_model(name), bf16=True, channels_last=True)
+        b = plan_buckets(L, 5)
+        assert b[0][1] == L.ntiles and b[-1][0] == 0
+        for (t0, t1, idxs), (u0, u1, jdxs) in zip(b[:-1], b[1:]):
+            assert u1 == t0 and max(jdxs) < min(idxs)            # contiguous, later buckets hold earlier layers
+        assert sorted(i for _, _, idxs in b for i in idxs) == list(range(L.ntensors))
+        assert len(b) <= 8
+        if name != "LeNet":
+            assert (b[-1][1] - b[-1][0]) <= 0.12 * L.ntiles      # the exposed tail bucket is small
+
+
+def test_ops_fall_back_to_aten_on_cpu():
+    torch.manual_seed(0)
+    x = torch.randn(4, 64, 8, 8)
+    conv, ref = Conv2d(64, 128, 1, bias=False), torch.nn.Conv2d(64, 128, 1, bias=False)
+    ref.load_state_dict(conv.state_dict())
+    assert torch.equal(conv(x), ref(x))
+    bn, rbn = FusedBatchNorm2d(64), torch.nn.BatchNorm2d(64)
+    res = torch.randn_like(x)
+    y = bn(x, residual=res, relu=True)
+    assert torch.allclose(y, F.relu(rbn(x) + res), atol=1e-6)
+    assert torch.allclose(bn.running_var, rbn.running_var) and int(bn.num_batches_tracked) == 1
+    lin, rl = Linear(64, 10), torch.nn.Linear(64, 10)
+    rl.load_state_dict(lin.state_dict())
+    assert torch.equal(lin(x.mean((2, 3))), rl(x.mean((2, 3))))
+    # state_dict keys are the reference's (nn.Module naming)
+    keys = set(build_model("ResNet18").state_dict())
+    assert {"conv1.weight", "bn1.running_mean", "layer1.0.conv1.weight", "layer2.0.shortcut.1.weight", "linear.bias"} <= keys
+    vkeys = set(build_model("VGG11").state_dict())
+    assert {"features.0.weight", "features.1.running_var", "features.4.weight", "classifier.1.weight", "classifier.6.bias"} <= vkeys
