@@ -42,6 +42,69 @@ class _Conv1x1Fn(torch.autograd.Function):
         return dx, dw, db
 
 
+def _lib():
+    import ctypes as C
+    from .. import _native as N
+    lib = N.cuda()
+    if not getattr(lib, "_conv_ready", False):
+        lib.drc_conv3x3_supported.argtypes = [C.c_int] * 5
+        lib.drc_conv3x3_supported.restype = C.c_int
+        lib.drc_conv3x3.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 6 + [N.ptr, N.ptr, C.c_int, C.c_int, N.ptr]
+        lib.drc_conv3x3.restype = C.c_int
+        lib._conv_ready = True
+    return lib
+
+
+def conv3x3_tcgen05(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution (``dgrad=False``) or its backward-data pass (``dgrad=True``) on the tcgen05
+    implicit-GEMM kernel (csrc/cuda/conv_tcgen05.cu).  ``act``: channels-last bf16 [N, C, H, W]; ``weight``:
+    [Cout, Cin, 3, 3] in channels-last storage ([Cout, 3, 3, Cin] in memory, the arena layout)."""
+    from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
+    n, _, h, w = act.shape
+    cout, cin = weight.shape[0], weight.shape[1]
+    assert act.is_contiguous(memory_format=torch.channels_last) and weight.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((n, cin if dgrad else cout, h, w), dtype=torch.bfloat16, device=act.device,
+                      memory_format=torch.channels_last)
+    bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
+    bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
+    N.check(lib.drc_conv3x3(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, cin, cout, int(dgrad), bf32, bb16,
+                            K.sm_count(act.device), act.device.index, torch.cuda.current_stream().cuda_stream), "conv3x3")
+    return out
+
+
+class _Conv3x3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return conv3x3_tcgen05(x, weight, False, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        cout, cin = weight.shape[0], weight.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if _lib().drc_conv3x3_supported(x.shape[2], x.shape[3], cin, cout, 1):
+                backend_counters["tcgen05"] += 1
+                dx = conv3x3_tcgen05(dy, weight, True)
+            else:
+                backend_counters["cudnn"] += 1
+                dx = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                         [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            # weight gradient: cuDNN's deterministic implicit-GEMM wgrad (K = N*H*W needs a split-K schedule; next step)
+            dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum((0, 2, 3))
+        return dx, dw, db
+
+
 class Conv2d(nn.Conv2d):
     """``nn.Conv2d`` (same parameters / state_dict) with the pointwise fast path described above."""
 
@@ -52,7 +115,18 @@ class Conv2d(nn.Conv2d):
                 and self.in_channels % 8 == 0 and self.out_channels % 8 == 0 and self.in_channels >= 64 and self.out_channels >= 64
                 and os.environ.get("DRACO_CONV1X1", "tcgen05") == "tcgen05")
 
+    def _conv3x3_ok(self, x: torch.Tensor) -> bool:
+        return (self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1) and self.dilation == (1, 1)
+                and self.groups == 1 and x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
+                and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+                and self.weight.is_contiguous(memory_format=torch.channels_last)
+                and os.environ.get("DRACO_CONV3X3", "cudnn") == "tcgen05"
+                and bool(_lib().drc_conv3x3_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, 0)))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._conv3x3_ok(x):
+            backend_counters["tcgen05"] += 1
+            return _Conv3x3Fn.apply(x, self.weight, self.bias)
         if not self._pointwise_ok(x):
             backend_counters["cudnn"] += 1
             return super().forward(x)

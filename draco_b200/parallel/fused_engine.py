@@ -159,8 +159,10 @@ class FusedEngine:
         """Enqueue everything this process contributes to one step.  Returns #kernels of ours launched."""
         cfg, L = self.cfg, self.layout
         n = 0
+        nvtx = torch.cuda.nvtx
         if self.local_workers:
             wc = self.worker
+            nvtx.range_push("draco/worker: fetch params + compute + encode/push")   # reference phases: Comm / Comp / Encode
             K.wait_flags([self.params_ready_ptr], self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_worker); n += 1
             if wc.bf16:
                 K.cast_params(L, wc.binder.params_f32, wc.binder.params_c); n += 1
@@ -232,7 +234,10 @@ class FusedEngine:
                 else:
                     K.push_encode(L, g32, g16, self.slot_ptr(w), flag=self.grad_flag_ptr(w), **push_kw)
                     n += 1
+        if self.local_workers:
+            nvtx.range_pop()
         if self.is_ps:
+            nvtx.range_push("draco/ps: gather + decode + update + broadcast")            # reference: Method / Update time
             base = self.flagsB.data_ptr()
             if self.pipeline_ps:
                 nb = len(self.worker.buckets)
@@ -249,6 +254,8 @@ class FusedEngine:
                 K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_ps); n += 1
                 n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
                                           dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
+        if self.is_ps:
+            nvtx.range_pop()
         K.step_add(self.step_dev, 1); n += 1
         return n
 

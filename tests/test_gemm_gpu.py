@@ -123,3 +123,42 @@ def test_pointwise_conv_on_tcgen05(n, cin, cout, hw):
     b2 = backend_counters["cudnn"]
     c3(x.detach())
     assert backend_counters["cudnn"] == b2 + 1
+
+
+@pytest.mark.parametrize("n,cin,cout,hw", [(4, 64, 64, 32), (8, 128, 128, 16), (16, 256, 256, 8), (32, 512, 512, 4), (5, 64, 128, 16),
+                                           (128, 64, 64, 32), (2, 512, 64, 2)])
+def test_conv3x3_tcgen05_fprop_and_dgrad(n, cin, cout, hw):
+    """TMA-patch implicit-GEMM 3x3 convolution (csrc/cuda/conv_tcgen05.cu) vs F.conv2d in fp32."""
+    from draco_b200.ops.conv import conv3x3_tcgen05
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(n + cin + cout + hw)
+    x = torch.randn(n, cin, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, 3, 3, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(cout, device=dev)
+    y = conv3x3_tcgen05(x, w, False, b)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel_err(y, ref) < 1.5e-2, _rel_err(y, ref)
+    dy = torch.randn(n, cout, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dx = conv3x3_tcgen05(dy, w, True)
+    dref = torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), padding=1)
+    assert _rel_err(dx, dref) < 1.5e-2, _rel_err(dx, dref)
+    assert torch.equal(conv3x3_tcgen05(x, w, False, b), y)            # deterministic
+
+
+def test_conv3x3_layer_autograd_path(monkeypatch):
+    from draco_b200.ops.conv import Conv2d, backend_counters
+    monkeypatch.setenv("DRACO_CONV3X3", "tcgen05")
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    conv = Conv2d(64, 128, 3, padding=1, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    x = torch.randn(16, 64, 16, 16, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    before = backend_counters["tcgen05"]
+    y = conv(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    assert backend_counters["tcgen05"] >= before + 2                  # fprop + dgrad
+    x32, w32 = x.detach().float().requires_grad_(True), conv.weight.detach().float().requires_grad_(True)
+    y32 = F.conv2d(x32, w32, padding=1)
+    y32.backward(gy.float())
+    assert _rel_err(y, y32) < 1.5e-2 and _rel_err(x.grad, x32.grad) < 2e-2 and _rel_err(conv.weight.grad, w32.grad) < 2e-2
