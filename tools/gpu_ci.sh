@@ -22,6 +22,7 @@ for s in $STAGES; do
     worker) timeout -k 10 600 python tools/bench_worker.py > gpurun_out/bench_worker.log 2>&1; echo "worker rc=$?" ;;
     diag) timeout -k 10 120 python tools/diag_flags.py > gpurun_out/diag_flags.log 2>&1; echo "diag rc=$?" ;;
     norm) timeout -k 10 300 python -m pytest tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/t_norm.log 2>&1; echo "norm rc=$?" ;;
+    convbench) timeout -k 10 300 python tools/bench_conv.py > gpurun_out/conv_bench.log 2>&1; echo "convbench rc=$?" ;;
     alltests) timeout -k 10 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "alltests rc=$?" ;;
   esac
 done
