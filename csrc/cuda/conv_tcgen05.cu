@@ -289,6 +289,184 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// wgrad:  dW[co, r, s, ci] = sum_{n,h,w} dy[n,h,w,co] * x[n, h+r-1, w+s-1, ci]
+//
+// GEMM view per filter tap: M = Cout, N = Cin, K = N*H*W pixels.  Both operands are MN-major: a K-block is a 64-pixel
+// patch, the A tile is the dy patch [64 px][co] and the B tile is the x patch shifted by the tap [64 px][ci] -- both are
+// exactly what a 4-D TMA box delivers (rows = pixels, 128-byte rows of 64 channels), again with the halo zero-filled.
+// K is huge and the number of output tiles tiny (9 taps x Cout/128 x Cin/BLOCK_N), so the K range is split across CTAs;
+// every split writes its fp32 partial tile and `wgrad_reduce_kernel` folds the splits in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  int N, H, W, Cin, Cout;
+  int PW, PH, PN;               // 64-pixel patch shape
+  int splits;                   // K splits
+  float* partial;               // [splits][Cout][9*Cin]
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgradArgs a) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;            // 2 atoms of [64 px][64 co]
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wt = a.W / a.PW, ht = a.H / a.PH, nt = (a.N + a.PN - 1) / a.PN;
+  const int k_total = wt * ht * nt;                          // 64-pixel K-blocks
+  const int m_tiles = (a.Cout + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.Cin + BLOCK_N - 1) / BLOCK_N;
+  const int out_tiles = m_tiles * 9 * n_tiles;
+  const int num_work = out_tiles * a.splits;
+  const int k_per_split = (k_total + a.splits - 1) / a.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  // work item -> (split, m tile, tap, n tile); splits of one output tile are spread over different CTAs
+  auto decode = [&](int wi, int& split, int& co0, int& tap, int& ci0) {
+    split = wi / out_tiles;
+    int t = wi - split * out_tiles;
+    const int ntile = t % n_tiles; t /= n_tiles;
+    tap = t % 9; t /= 9;
+    co0 = t * BLOCK_M; ci0 = ntile * BLOCK_N;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+        int split, co0, tap, ci0; decode(wi, split, co0, tap, ci0);
+        const int r = tap / 3, s = tap - 3 * r;
+        const int kb0 = split * k_per_split, kb1 = min(k_total, kb0 + k_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int w0 = (kb % wt) * a.PW, h0 = ((kb / wt) % ht) * a.PH, n0 = (kb / (wt * ht)) * a.PN;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          // a 64-channel atom entirely beyond Cout is never read back: skip its load (its TMEM rows hold junk)
+          const int a_atoms = min(BLOCK_M / 64, (a.Cout - co0 + 63) / 64);
+          mbar_expect_tx(&full_bar[stage], a_atoms * (BLOCK_K * 128) + B_BYTES);
+          for (int j = 0; j < a_atoms; ++j) tma_load_4d(sa + j * (BLOCK_K * 128), &tmap_dy, co0 + 64 * j, w0, h0, n0, &full_bar[stage]);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_4d(sb + j * (BLOCK_K * 128), &tmap_x, ci0 + 64 * j, w0 + s - 1, h0 + r - 1, n0, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      uint32_t idesc = make_idesc<BLOCK_N, true>();
+      idesc |= 1u << 15;                                      // A is MN-major too
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+        int split, co0, tap, ci0; decode(wi, split, co0, tap, ci0);
+        const int kb0 = split * k_per_split, kb1 = min(k_total, kb0 + k_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t da = make_smem_desc<true>(sa), db = make_smem_desc<true>(sb);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 128) >> 4);
+            umma_f16(tmem_d, da + adv, db + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    const long long row_pitch = 9LL * a.Cin;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      int split, co0, tap, ci0; decode(wi, split, co0, tap, ci0);
+      const int kb0 = split * k_per_split, kb1 = min(k_total, kb0 + k_per_split);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int co = co0 + q * 32 + lane;
+      float* orow = a.partial + ((long long)split * a.Cout + co) * row_pitch + (long long)tap * a.Cin;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
+        const int col0 = ci0 + c;
+        if (co < a.Cout && col0 < a.Cin) {
+          // an empty K range (more splits than K-blocks) must still produce zeros
+          const bool empty = kb1 <= kb0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j + 4 <= a.Cin) {
+              float4 o = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                               : make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              *reinterpret_cast<float4*>(orow + col0 + j) = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* partial, int splits, long long elems, __nv_bfloat16* out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= elems) return;
+  float4 acc = *reinterpret_cast<const float4*>(partial + i);
+  for (int s = 1; s < splits; ++s) {                           // fixed order: bit-deterministic
+    float4 v = *reinterpret_cast<const float4*>(partial + (long long)s * elems + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(out + i) = o;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -383,4 +561,75 @@ extern "C" int drc_conv3x3(const void* act, const void* wgt, void* out, int N, i
     }
   }
   return block_n == 64 ? launch<64, true>(tx, tw, a, num_sms, stream) : launch<128, true>(tx, tw, a, num_sms, stream);
+}
+
+// number of K splits and fp32 workspace elements for wgrad
+extern "C" int drc_conv3x3_wgrad_plan(int N, int H, int W, int Cin, int Cout, int num_sms, long long* ws_elems) {
+  const int block_n = Cin >= 128 ? 128 : 64;
+  const int out_tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * 9 * ((Cin + block_n - 1) / block_n);
+  int PW = W < 64 ? W : 64, PH = (64 / PW) < H ? (64 / PW) : H, PN = 64 / (PW * PH);
+  const int k_total = (W / PW) * (H / PH) * ((N + PN - 1) / PN);
+  int splits = num_sms / out_tiles;                            // one wave: out_tiles * splits <= SMs
+  if (splits > k_total) splits = k_total;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  if (ws_elems) *ws_elems = (long long)splits * Cout * 9 * Cin;
+  return splits;
+}
+
+extern "C" int drc_conv3x3_wgrad_supported(int H, int W, int Cin, int Cout) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  if (!pow2(W) || !pow2(H) || W > 64) return 0;
+  if (Cin % 64 || Cout % 64) return 0;
+  if (W * H < 64 && 64 % (W * H)) return 0;
+  return 1;
+}
+
+// dy: [N,H,W,Cout] bf16, x: [N,H,W,Cin] bf16 -> dw: [Cout,3,3,Cin] bf16 (arena layout).  ws: fp32 workspace from the plan.
+extern "C" int drc_conv3x3_wgrad(const void* dy, const void* x, void* dw, float* ws, int N, int H, int W, int Cin, int Cout,
+                                 int num_sms, int device, cudaStream_t stream) {
+  if (!drc_conv3x3_wgrad_supported(H, W, Cin, Cout)) return -1;
+  if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -2;
+  WgradArgs a;
+  a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+  a.PW = W < 64 ? W : 64; a.PH = (64 / a.PW) < H ? (64 / a.PW) : H; a.PN = 64 / (a.PW * a.PH);
+  a.splits = drc_conv3x3_wgrad_plan(N, H, W, Cin, Cout, num_sms, nullptr);
+  a.partial = ws;
+  const int block_n = Cin >= 128 ? 128 : 64;
+  CUtensorMap tdy, tx;
+  for (int which = 0; which < 2; ++which) {
+    const int C = which ? Cin : Cout;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)a.PW, (cuuint32_t)a.PH, (cuuint32_t)a.PN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(which ? &tx : &tdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(which ? x : dy), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1000 * (which + 1) + (int)r;
+  }
+  const int out_tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * 9 * ((Cin + block_n - 1) / block_n);
+  const int work = out_tiles * a.splits;
+  const int grid = work < num_sms ? work : num_sms;
+  int rc;
+  if (block_n == 64) {
+    constexpr int BN_ = 64, SB = BLOCK_M * BLOCK_K * 2 + BN_ * BLOCK_K * 2, ST = (200 * 1024) / SB > 8 ? 8 : (200 * 1024) / SB, SM = ST * SB + 1280;
+    auto kern = conv3x3_wgrad_tcgen05_kernel<BN_, ST>;
+    static bool cfgd = false;
+    if (!cfgd) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); if (e != cudaSuccess) return (int)e; cfgd = true; }
+    kern<<<grid, NUM_THREADS, SM, stream>>>(tdy, tx, a);
+  } else {
+    constexpr int BN_ = 128, SB = BLOCK_M * BLOCK_K * 2 + BN_ * BLOCK_K * 2, ST = (200 * 1024) / SB > 8 ? 8 : (200 * 1024) / SB, SM = ST * SB + 1280;
+    auto kern = conv3x3_wgrad_tcgen05_kernel<BN_, ST>;
+    static bool cfgd = false;
+    if (!cfgd) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); if (e != cudaSuccess) return (int)e; cfgd = true; }
+    kern<<<grid, NUM_THREADS, SM, stream>>>(tdy, tx, a);
+  }
+  rc = (int)cudaGetLastError();
+  if (rc) return rc;
+  const long long elems = (long long)Cout * 9 * Cin;
+  wgrad_reduce_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, stream>>>(ws, a.splits, elems, (__nv_bfloat16*)dw);
+  return (int)cudaGetLastError();
 }

@@ -5,8 +5,8 @@ im2col, no layout change (weights live in the arena as ``[Cout, kH, kW, Cin]``).
 ``csrc/cuda/gemm_tcgen05.cu`` exactly like a Linear layer (ops/linear.py): fprop K-major x K-major, dgrad with an
 MN-major B, wgrad with MN-major A and B (K = N*H*W).  This covers two thirds of the convolutions of the bottleneck
 ResNets (50/101/152: conv1, conv3 and the stride-1 projection shortcuts).  Everything else -- 3x3, strided -- goes to
-cuDNN's implicit-GEMM kernels in deterministic mode (the TMA-im2col tcgen05 convolution is the next item of the build
-plan).  ``backend_counters`` records which path served each call.
+cuDNN's implicit-GEMM kernels in deterministic mode unless ``DRACO_CONV3X3=tcgen05`` selects the TMA-patch implicit-GEMM
+kernels of ``csrc/cuda/conv_tcgen05.cu`` (fprop, dgrad and split-K wgrad) for the 3x3 / stride-1 layers.  ``backend_counters`` records which path served each call.
 
 Reference counterpart: ``nn.Conv2d`` inside src/model_ops/resnet.py:14-64 / vgg.py:46-59 (PyTorch-0.3 CPU THNN).
 """
@@ -51,8 +51,35 @@ def _lib():
         lib.drc_conv3x3_supported.restype = C.c_int
         lib.drc_conv3x3.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 6 + [N.ptr, N.ptr, C.c_int, C.c_int, N.ptr]
         lib.drc_conv3x3.restype = C.c_int
+        lib.drc_conv3x3_wgrad_supported.argtypes = [C.c_int] * 4
+        lib.drc_conv3x3_wgrad_supported.restype = C.c_int
+        lib.drc_conv3x3_wgrad_plan.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_longlong)]
+        lib.drc_conv3x3_wgrad_plan.restype = C.c_int
+        lib.drc_conv3x3_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 7 + [N.ptr]
+        lib.drc_conv3x3_wgrad.restype = C.c_int
         lib._conv_ready = True
     return lib
+
+
+def conv3x3_wgrad_tcgen05(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Weight gradient of the 3x3 / stride 1 / pad 1 convolution on the split-K tcgen05 kernel: both operands are read
+    MN-major straight from the NHWC activations (K = pixels), fp32 partials are folded in a fixed order.  Returns
+    [Cout, Cin, 3, 3] in channels-last storage (the arena layout)."""
+    import ctypes as C
+    from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
+    n, cout, h, w = dy.shape
+    cin = x.shape[1]
+    assert dy.is_contiguous(memory_format=torch.channels_last) and x.is_contiguous(memory_format=torch.channels_last)
+    sms = K.sm_count(dy.device)
+    ws_elems = C.c_longlong(0)
+    lib.drc_conv3x3_wgrad_plan(n, h, w, cin, cout, sms, C.byref(ws_elems))
+    ws = torch.empty(ws_elems.value, dtype=torch.float32, device=dy.device)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+    N.check(lib.drc_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, w, cin, cout, sms,
+                                  dy.device.index, torch.cuda.current_stream().cuda_stream), "conv3x3_wgrad")
+    return dw
 
 
 def conv3x3_tcgen05(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None) -> torch.Tensor:
@@ -97,9 +124,14 @@ class _Conv3x3Fn(torch.autograd.Function):
                 dx = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
                                                          [True, False, False])[0]
         if ctx.needs_input_grad[1]:
-            # weight gradient: cuDNN's deterministic implicit-GEMM wgrad (K = N*H*W needs a split-K schedule; next step)
-            dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-                                                     [False, True, False])[1]
+            if (os.environ.get("DRACO_CONV3X3_WGRAD", "tcgen05") == "tcgen05"
+                    and _lib().drc_conv3x3_wgrad_supported(x.shape[2], x.shape[3], cin, cout)):
+                backend_counters["tcgen05"] += 1
+                dw = conv3x3_wgrad_tcgen05(dy, x)
+            else:
+                backend_counters["cudnn"] += 1
+                dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                         [False, True, False])[1]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum((0, 2, 3))
         return dx, dw, db

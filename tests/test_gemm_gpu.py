@@ -146,6 +146,22 @@ def test_conv3x3_tcgen05_fprop_and_dgrad(n, cin, cout, hw):
     assert torch.equal(conv3x3_tcgen05(x, w, False, b), y)            # deterministic
 
 
+@pytest.mark.parametrize("n,cin,cout,hw", [(4, 64, 64, 32), (128, 64, 64, 32), (128, 128, 128, 16), (64, 256, 256, 8), (128, 512, 512, 4),
+                                           (5, 64, 128, 16), (7, 512, 64, 2), (3, 128, 192, 4)])
+def test_conv3x3_tcgen05_wgrad(n, cin, cout, hw):
+    """split-K weight gradient (MN-major dy and x patches through 4-D TMA) vs conv2d_weight in fp32."""
+    from draco_b200.ops.conv import conv3x3_wgrad_tcgen05
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(n * 3 + cin + cout + hw)
+    x = torch.randn(n, cin, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(n, cout, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dw = conv3x3_wgrad_tcgen05(dy, x)
+    ref = torch.nn.grad.conv2d_weight(x.float(), (cout, cin, 3, 3), dy.float(), padding=1)
+    assert dw.shape == ref.shape and dw.is_contiguous(memory_format=torch.channels_last)
+    assert _rel_err(dw, ref) < 1.5e-2, _rel_err(dw, ref)
+    assert torch.equal(conv3x3_wgrad_tcgen05(dy, x), dw)              # deterministic split-K
+
+
 def test_conv3x3_layer_autograd_path(monkeypatch):
     from draco_b200.ops.conv import Conv2d, backend_counters
     monkeypatch.setenv("DRACO_CONV3X3", "tcgen05")
@@ -157,7 +173,7 @@ def test_conv3x3_layer_autograd_path(monkeypatch):
     y = conv(x)
     gy = torch.randn_like(y)
     y.backward(gy)
-    assert backend_counters["tcgen05"] >= before + 2                  # fprop + dgrad
+    assert backend_counters["tcgen05"] >= before + 3                  # fprop + dgrad + wgrad
     x32, w32 = x.detach().float().requires_grad_(True), conv.weight.detach().float().requires_grad_(True)
     y32 = F.conv2d(x32, w32, padding=1)
     y32.backward(gy.float())

@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from draco_b200.ops.conv import conv3x3_tcgen05  # noqa: E402
+from draco_b200.ops.conv import conv3x3_tcgen05, conv3x3_wgrad_tcgen05  # noqa: E402
 
 torch.backends.cudnn.deterministic = True
 torch.backends.cudnn.benchmark = False
@@ -37,7 +37,9 @@ for (n, c, k, hw) in [(128, 64, 64, 32), (128, 128, 128, 16), (128, 256, 256, 8)
     t_fc = timeit(lambda: F.conv2d(x, w, padding=1))
     t_d = timeit(lambda: conv3x3_tcgen05(dy, w, True))
     t_dc = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False]))
-    rows.append({"N": n, "Cin": c, "Cout": k, "HW": hw, "fprop_us": t_f, "cudnn_fprop_us": t_fc, "dgrad_us": t_d, "cudnn_dgrad_us": t_dc,
+    t_w = timeit(lambda: conv3x3_wgrad_tcgen05(dy, x))
+    t_wc = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False]))
+    rows.append({"wgrad_us": t_w, "cudnn_wgrad_us": t_wc, "N": n, "Cin": c, "Cout": k, "HW": hw, "fprop_us": t_f, "cudnn_fprop_us": t_fc, "dgrad_us": t_d, "cudnn_dgrad_us": t_dc,
                  "fprop_tflops": fl / t_f / 1e6, "cudnn_fprop_tflops": fl / t_fc / 1e6})
     print(rows[-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
