@@ -70,7 +70,23 @@ class CollectiveEngine:
 
     # ------------------------------------------------------------------ phases
     def _broadcast_params(self) -> None:
-        if self.nprocs > 1:
+        if self.nprocs > 1 and self.cfg.comm_type == "Async":
+            # --comm-type=Async: the PS posts one point-to-point send per (parameter tensor, worker process) instead of a
+            # broadcast (reference: async_bcast_layer_weights_async, baseline_master.py:164-178 <-> baseline_worker.py:171-188).
+            # Like the reference's, the step stays fully synchronous -- only the fan-out primitive differs.
+            ops = []
+            peers = [p for p in self.place.worker_procs() if p != 0]
+            for i in range(self.layout.ntensors):
+                s = self.layout.specs[i]
+                view = self.params_f32[s.offset: s.offset + s.numel]
+                if self.is_ps:
+                    ops += [dist.P2POp(dist.isend, view, p, group=self.group) for p in peers]
+                elif self.rank in peers:
+                    ops.append(dist.P2POp(dist.irecv, view, 0, group=self.group))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+        elif self.nprocs > 1:
             for i in range(self.layout.ntensors):
                 s = self.layout.specs[i]
                 dist.broadcast(self.params_f32[s.offset: s.offset + s.numel], src=0, group=self.group)

@@ -145,12 +145,12 @@ def _free_port():
     return p
 
 
-def _gloo_worker(rank, world, port, compress, q):
+def _gloo_worker(rank, world, port, compress, q, comm_type="Bcast"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg = JobConfig(network="LeNet", dataset="MNIST", approach="maj_vote", mode="maj_vote", group_size=1, worker_fail=0,
                     err_mode="none", batch_size=32, max_steps=12, transport="gloo", lr=0.05, momentum=0.9, synthetic_size=512,
-                    eval_freq=10 ** 6, compress_grad="compress" if compress else "None")
+                    eval_freq=10 ** 6, compress_grad="compress" if compress else "None", comm_type=comm_type)
     t = Trainer(cfg, rank=rank, world=world, device=torch.device("cpu"), quiet=True)
     losses, sums = [], []
     for _ in range(12):
@@ -164,12 +164,12 @@ def _gloo_worker(rank, world, port, compress, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("compress", [False, True])
-def test_gloo_ps_plus_two_workers(compress):
+@pytest.mark.parametrize("compress,comm_type", [(False, "Bcast"), (True, "Bcast"), (False, "Async")])
+def test_gloo_ps_plus_two_workers(compress, comm_type):
     world, port = 3, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, compress, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, compress, q, comm_type)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=240) for _ in range(world))
