@@ -12,13 +12,13 @@
 
 struct UpdateArgs {
   // gradient source ---------------------------------------------------------------------------
-  int mode;                       // 0: select-sum over `select` table; 1: cyclic recombination
+  int mode;                       // 0: select-sum over `select` table; 1: cyclic recombination; 2: real per-tensor weights
   const float* grad_in;           // mode 0: [P][slot_stride] fp32 ; mode 1: [n][2*slot_stride] complex64
   long long slot_stride;          // elements (fp32 words for mode 0, complex elements for mode 1)
   const int* select;              // mode 0: [K][T] worker slot to read for (k, tensor); null -> rows 0..K-1 for all tensors
   int K;                          // mode 0: rows summed per tensor ; mode 1: n workers
   float scale;                    // 1/K (mean, vote), 1 (krum, median vector), 1/n (cyclic)
-  const float2* recomb;           // mode 1: [T][n] recombination vector v (float2 = complex64)
+  const float2* recomb;           // mode 1: [T][n] recombination vector v (float2 = complex64); mode 2: float [T][K] weights
   TileView tv;
   // optimizer ---------------------------------------------------------------------------------
   float* params;                  // PS master fp32 [D]
@@ -51,6 +51,13 @@ __global__ void __launch_bounds__(DRC_THREADS) aggregate_update_kernel(const __g
         const int slot = a.select ? a.select[k * a.tv.ntensors + tensor] : k;
         float4 v = ld_f4(reinterpret_cast<const float4*>(a.grad_in + slot * a.slot_stride + idx));
         g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
+    } else if (MODE == 2) {
+      const float* wts = reinterpret_cast<const float*>(a.recomb);    // geometric median: sum_k w[tensor][k] * g_k
+      for (int k = 0; k < a.K; ++k) {
+        const float w = wts[tensor * a.K + k];
+        float4 v = ld_f4(reinterpret_cast<const float4*>(a.grad_in + k * a.slot_stride + idx));
+        g.x = fmaf(w, v.x, g.x); g.y = fmaf(w, v.y, g.y); g.z = fmaf(w, v.z, g.z); g.w = fmaf(w, v.w, g.w);
       }
     } else {
       for (int k = 0; k < a.K; ++k) {
@@ -98,6 +105,7 @@ __global__ void __launch_bounds__(DRC_THREADS) aggregate_update_kernel(const __g
 extern "C" int drc_aggregate_update(const UpdateArgs* args, int grid, cudaStream_t stream) {
   if (args->ndst > DRC_MAX_DST || args->flags.n > DRC_MAX_DST) return (int)cudaErrorInvalidValue;
   if (args->mode == 0) aggregate_update_kernel<0><<<grid, DRC_THREADS, 0, stream>>>(*args);
+  else if (args->mode == 2) aggregate_update_kernel<2><<<grid, DRC_THREADS, 0, stream>>>(*args);
   else aggregate_update_kernel<1><<<grid, DRC_THREADS, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }

@@ -7,6 +7,15 @@
 // ||m_new - m||^2 for the stopping rule, so every iteration reads the P x D slab exactly once.  A tiny
 // `geomed_prep_kernel` turns the accumulated distances into weights and freezes converged tensors.
 //
+// The product path does better than one pass per iteration: every Weiszfeld iterate is a convex combination
+// m = sum_j w_j g_j of the inputs, and for such a point
+//     ||g_i - m||^2 = sum_j w_j D_ij - 1/2 sum_jk w_j w_k D_jk          (D_ij = ||g_i - g_j||^2),
+// so the whole iteration lives in the P-dimensional weight space once the P(P-1)/2 pairwise distances are known.
+// `pair_dist_kernel` (shared with Krum) reads the slab ONCE, `geomed_weights_kernel` iterates to convergence on one
+// warp per tensor in fp64, and the weighted combination is formed inside the fused SGD + broadcast kernel
+// (aggregate_update MODE 2): two passes over the P x D slab instead of one per iteration.  The streaming
+// per-iteration kernels below remain for P > 16.
+//
 // Krum -- reference: double Python loop of np.linalg.norm per tensor (baseline_master.py:278-296).  Here one
 // pass produces all P(P-1)/2 squared distances per tensor, a one-thread-per-tensor kernel scores and selects,
 // and the winner row goes through the fused select + SGD + broadcast kernel.
@@ -145,12 +154,12 @@ struct PairDistArgs {
 };
 
 __global__ void __launch_bounds__(DRC_THREADS) pair_dist_kernel(const __grid_constant__ PairDistArgs a) {
-  __shared__ float s_acc[KRUM_MAXPAIRS];
+  __shared__ double s_acc[KRUM_MAXPAIRS];
   const int npairs = a.P * (a.P - 1) / 2;
   for (int tile = blockIdx.x; tile < a.tv.ntiles; tile += gridDim.x) {
     int tensor;
     const int valid = tile_valid(a.tv, tile, tensor);
-    for (int q = threadIdx.x; q < npairs; q += DRC_THREADS) s_acc[q] = 0.f;
+    for (int q = threadIdx.x; q < npairs; q += DRC_THREADS) s_acc[q] = 0.0;
     __syncthreads();
     const long long idx = (long long)tile * DRC_TILE + threadIdx.x * 4;
     const bool active = (int)threadIdx.x * 4 < valid;
@@ -170,13 +179,13 @@ __global__ void __launch_bounds__(DRC_THREADS) pair_dist_kernel(const __grid_con
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-          if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[j * (j - 1) / 2 + i], d);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[j * (j - 1) / 2 + i], (double)d);   // fp64 from the warp level up
         }
       }
     }
     __syncthreads();
     for (int q = threadIdx.x; q < npairs; q += DRC_THREADS)
-      atomicAdd(&a.pair_d2[(long long)tensor * npairs + q], (double)s_acc[q]);
+      atomicAdd(&a.pair_d2[(long long)tensor * npairs + q], s_acc[q]);
     __syncthreads();
   }
 }
@@ -221,6 +230,75 @@ extern "C" int drc_krum_select(const KrumSelectArgs* args, cudaStream_t stream) 
   krum_select_kernel<<<(args->T + 63) / 64, 64, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Weiszfeld in weight space (one warp per tensor, lane i owns input i; fp64)
+// ---------------------------------------------------------------------------------------------
+struct GeoMedWeightsArgs {
+  double* pair_d2;                // [T][P(P-1)/2] consumed and zeroed
+  int T, P, max_iter;
+  double eps;                     // stop when no weight moved by more than eps
+  float* weights;                 // [T][P] out, sum to 1
+  int* iters;                     // [T] out (optional): iterations used
+};
+
+__global__ void geomed_weights_kernel(const __grid_constant__ GeoMedWeightsArgs a) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= a.T) return;
+  const int npairs = a.P * (a.P - 1) / 2;
+  double* d2 = a.pair_d2 + (long long)t * npairs;
+  double row[KRUM_MAXP];
+  double maxd = 0.0;
+#pragma unroll
+  for (int j = 0; j < KRUM_MAXP; ++j) {
+    row[j] = 0.0;
+    if (j < a.P && lane < a.P && j != lane) {
+      const int lo = lane < j ? lane : j, hi = lane < j ? j : lane;
+      row[j] = d2[hi * (hi - 1) / 2 + lo];
+      maxd = fmax(maxd, row[j]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxd = fmax(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+  __syncwarp();
+  for (int q = lane; q < npairs; q += 32) d2[q] = 0.0;
+  double w = lane < a.P ? 1.0 / a.P : 0.0;            // first estimate: the mean
+  int it = 0;
+  if (maxd > 0.0) {
+    const double floor_d = 1e-12 * sqrt(maxd) + 1e-300;
+    for (; it < a.max_iter; ++it) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < KRUM_MAXP; ++j)
+        if (j < a.P) s = fma(__shfl_sync(0xffffffffu, w, j), row[j], s);
+      double q = w * s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const double dist = fmax(sqrt(fmax(s - 0.5 * q, 0.0)), floor_d);
+      double wn = lane < a.P ? 1.0 / dist : 0.0;
+      double sum = wn;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      wn /= sum;
+      double delta = fabs(wn - w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) delta = fmax(delta, __shfl_xor_sync(0xffffffffu, delta, o));
+      w = wn;
+      if (delta <= a.eps) { ++it; break; }
+    }
+  }
+  if (lane < a.P) a.weights[t * a.P + lane] = (float)w;
+  if (a.iters && lane == 0) a.iters[t] = it;
+}
+
+extern "C" int drc_geomed_weights(const GeoMedWeightsArgs* args, cudaStream_t stream) {
+  if (args->P > KRUM_MAXP) return (int)cudaErrorInvalidValue;
+  geomed_weights_kernel<<<(args->T * 32 + 127) / 128, 128, 0, stream>>>(*args);
+  return (int)cudaGetLastError();
+}
+extern "C" int drc_sizeof_GeoMedWeightsArgs() { return (int)sizeof(GeoMedWeightsArgs); }
 
 extern "C" int drc_sizeof_GeoMedArgs() { return (int)sizeof(GeoMedArgs); }
 extern "C" int drc_sizeof_GeoMedPrepArgs() { return (int)sizeof(GeoMedPrepArgs); }

@@ -109,6 +109,11 @@ class GeoMedPrepArgs(C.Structure):
                 ("iter", C.c_int), ("eps", C.c_double)]
 
 
+class GeoMedWeightsArgs(C.Structure):
+    _fields_ = [("pair_d2", ptr), ("T", C.c_int), ("P", C.c_int), ("max_iter", C.c_int), ("eps", C.c_double), ("weights", ptr),
+                ("iters", ptr)]
+
+
 class PairDistArgs(C.Structure):
     _fields_ = [("grad_in", ptr), ("slot_stride", i64), ("P", C.c_int), ("tv", TileView), ("pair_d2", ptr)]
 
@@ -185,6 +190,7 @@ def cuda() -> C.CDLL:
             "drc_cyclic_locate": [C.POINTER(LocateArgs), st],
             "drc_geomed_iter": [C.POINTER(GeoMedArgs), C.c_int, st],
             "drc_geomed_prep": [C.POINTER(GeoMedPrepArgs), st],
+            "drc_geomed_weights": [C.POINTER(GeoMedWeightsArgs), st],
             "drc_pair_dist": [C.POINTER(PairDistArgs), C.c_int, st],
             "drc_krum_select": [C.POINTER(KrumSelectArgs), st],
             "drc_gemm_bf16": [ptr, i64, C.c_int, ptr, i64, C.c_int, ptr, i64, C.c_int, C.c_int, C.c_int, C.c_int, ptr, ptr,

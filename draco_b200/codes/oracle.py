@@ -64,6 +64,28 @@ def geometric_median(slots: np.ndarray, eps: float = 1e-8, max_iter: int = 200) 
     return m
 
 
+def geometric_median_weights(slots: np.ndarray, eps: float = 1e-10, max_iter: int = 256) -> np.ndarray:
+    """The same Weiszfeld iteration carried out on the convex weights only (host model of ``geomed_weights_kernel``,
+    csrc/cuda/robust.cu).  Every iterate is ``m = w @ X`` with ``sum(w) = 1``, for which
+    ``||x_i - m||^2 = (D w)_i - w^T D w / 2`` with ``D_ij = ||x_i - x_j||^2`` -- the data is touched once (for D)."""
+    X = np.asarray(slots, dtype=np.float64)
+    P = X.shape[0]
+    D = ((X[:, None, :] - X[None, :, :]) ** 2).sum(axis=2)
+    w = np.full(P, 1.0 / P)
+    if D.max() <= 0:
+        return w
+    floor_d = 1e-12 * np.sqrt(D.max()) + 1e-300
+    for _ in range(max_iter):
+        s = D @ w
+        d = np.maximum(np.sqrt(np.maximum(s - 0.5 * (w @ s), 0.0)), floor_d)
+        wn = (1.0 / d) / (1.0 / d).sum()
+        delta = np.abs(wn - w).max()
+        w = wn
+        if delta <= eps:
+            break
+    return w
+
+
 def krum_index(slots: np.ndarray, s: int) -> int:
     """Krum (arXiv:1703.02757) as the reference implements it (baseline_master.py:278-296):
     score_i = sum of the (P - s - 2) smallest squared distances to the others; argmin wins."""

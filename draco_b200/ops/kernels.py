@@ -132,10 +132,14 @@ def aggregate_update(layout: ArenaLayout, grad_in: Addr, slot_stride: int, *, pa
                      step_ptr: Addr, done_counter: Addr, K: int, scale: float, select: Addr = None,
                      recomb: Addr = None, first_step: int = 1, grad_out: Addr = None, mc_params: Addr = None,
                      dst: Sequence[Addr] = (), flags: Sequence[Addr] = (), grid: Optional[int] = None,
-                     tile_range: Optional[tuple] = None) -> None:
-    """Fused aggregate (select-sum or cyclic recombination) + SGD-momentum + parameter broadcast + flags."""
+                     tile_range: Optional[tuple] = None, weights: Addr = None) -> None:
+    """Fused aggregate (select-sum, cyclic recombination, or real per-tensor ``weights`` [T, K]) + SGD-momentum +
+    parameter broadcast + flags."""
     a = N.UpdateArgs()
-    a.mode = 1 if recomb is not None else 0
+    a.mode = 1 if recomb is not None else (2 if weights is not None else 0)
+    if weights is not None:
+        assert recomb is None and select is None
+        recomb = weights
     a.grad_in = addr(grad_in)
     a.slot_stride = slot_stride
     a.select = addr(select)
@@ -236,6 +240,25 @@ def geometric_median(layout: ArenaLayout, grad_in: Addr, slot_stride: int, P: in
                           ws.dist2.data_ptr(), ws.move2.data_ptr())
         N.check(lib.drc_geomed_iter(C.byref(ga), grid, _stream()), "geomed_iter")
     return ws.median
+
+
+GEOMED_FAST_MAXP = 16
+
+
+def geometric_median_weights(layout: ArenaLayout, grad_in: Addr, slot_stride: int, P: int, pair_d2: torch.Tensor,
+                             weights: torch.Tensor, max_iter: int = 256, eps: float = 1e-10,
+                             iters_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-tensor geometric median as convex weights: ``median_t = sum_i weights[t, i] * slot_i`` (Weiszfeld run in weight
+    space from the pairwise distances -- one pass over the slab; see csrc/cuda/robust.cu).  ``pair_d2``: zeroed fp64
+    [T, P(P-1)/2] scratch (left zeroed); ``weights``: fp32 [T, P] out."""
+    assert P <= GEOMED_FAST_MAXP
+    lib = N.cuda()
+    pa = N.PairDistArgs(addr(grad_in), slot_stride, P, layout.tile_view(weights.device), pair_d2.data_ptr())
+    N.check(lib.drc_pair_dist(C.byref(pa), stream_grid(layout, 4), _stream()), "pair_dist")
+    wa = N.GeoMedWeightsArgs(pair_d2.data_ptr(), layout.ntensors, P, max_iter, eps, weights.data_ptr(),
+                             iters_out.data_ptr() if iters_out is not None else None)
+    N.check(lib.drc_geomed_weights(C.byref(wa), _stream()), "geomed_weights")
+    return weights
 
 
 def krum_select(layout: ArenaLayout, grad_in: Addr, slot_stride: int, P: int, s: int, pair_d2: torch.Tensor,

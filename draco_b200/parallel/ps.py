@@ -69,7 +69,12 @@ class FusedPS:
             self.pair_d2 = torch.zeros(T, self.P * (self.P - 1) // 2, dtype=torch.float64, device=device)
             self.select = torch.zeros(T, dtype=torch.int32, device=device)
         elif self.rule == "geomedian":
-            self.gm = K.GeoMedianWorkspace(layout, self.P, device)
+            if self.P <= K.GEOMED_FAST_MAXP:      # weight-space Weiszfeld: 2 passes over the slab in total
+                self.gm = None
+                self.pair_d2 = torch.zeros(T, self.P * (self.P - 1) // 2, dtype=torch.float64, device=device)
+                self.gm_weights = torch.zeros(T, self.P, dtype=torch.float32, device=device)
+            else:
+                self.gm = K.GeoMedianWorkspace(layout, self.P, device)
         elif self.rule == "cyclic":
             self.code = code
             self.E = torch.zeros(T, self.P, 2, dtype=torch.float64, device=device)
@@ -116,6 +121,9 @@ class FusedPS:
         elif self.rule == "krum":
             K.krum_select(L, self.grad_in, self.slot_stride, self.P, self.cfg.worker_fail, self.pair_d2, self.select); n += 2
             K.aggregate_update(L, self.grad_in, self.slot_stride, K=1, scale=1.0, select=self.select, **common); n += 1
+        elif self.rule == "geomedian" and self.gm is None:
+            K.geometric_median_weights(L, self.grad_in, self.slot_stride, self.P, self.pair_d2, self.gm_weights); n += 2
+            K.aggregate_update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0, weights=self.gm_weights, **common); n += 1
         elif self.rule == "geomedian":
             iters = 48
             K.geometric_median(L, self.grad_in, self.slot_stride, self.P, self.gm, iters=iters); n += 2 * iters + 1

@@ -175,3 +175,25 @@ def test_adam_modified_matches_torch_adam():
         ref.step()
         new.step(grads=[g], mode="normal")
     assert torch.allclose(p_ref[0].detach(), p_new[0], atol=1e-6)
+
+
+def test_geometric_median_in_weight_space_matches_weiszfeld():
+    """Host model of the one-pass device algorithm: Weiszfeld on convex weights from pairwise distances."""
+    rng = np.random.RandomState(5)
+    for n in (3, 40, 1500):
+        h = rng.randn(n) * 0.1
+        X = h[None] + 0.02 * rng.randn(7, n)
+        X[0] *= -100
+        X[3] = -100
+        w = oracle.geometric_median_weights(X)
+        assert abs(w.sum() - 1) < 1e-12 and w.min() >= 0
+        ref = oracle.geometric_median(X, eps=1e-12, max_iter=5000)
+        assert np.abs(w @ X - ref).max() < 1e-8
+    same = np.tile(rng.randn(1, 10), (5, 1))
+    assert np.allclose(oracle.geometric_median_weights(same), 0.2)
+    # the median sits on one of the inputs (3 identical points out of 5): the weights collapse onto them without NaN
+    X = rng.randn(5, 20)
+    X[1] = X[2] = X[0]
+    w = oracle.geometric_median_weights(X)
+    assert np.isfinite(w).all() and np.abs(w @ X - X[0]).max() < 1e-6
+

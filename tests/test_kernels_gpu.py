@@ -281,6 +281,38 @@ def test_geometric_median_kernel(K, dev):
     assert float(med[~torch.from_numpy(L.valid_mask()).to(dev)].abs().sum()) == 0
 
 
+def test_geometric_median_weight_space_kernel(K, dev):
+    """pairwise distances + Weiszfeld on the weights (one pass over the slab) against the fp64 oracle."""
+    L = small_layout()
+    P = 7
+    T = L.ntensors
+    honest = fill_valid(L, 1, dev, seed=21, scale=0.1)[0]
+    slots = honest[None] + 0.02 * fill_valid(L, P, dev, seed=22)
+    slots[1] = -100 * slots[1]
+    slots[4] = -100 * torch.from_numpy(L.valid_mask()).float().to(dev)
+    slots[6] = slots[6] + 3.0 * torch.from_numpy(L.valid_mask()).float().to(dev)
+    pair = torch.zeros(T, P * (P - 1) // 2, dtype=torch.float64, device=dev)
+    w = torch.zeros(T, P, dtype=torch.float32, device=dev)
+    its = torch.zeros(T, dtype=torch.int32, device=dev)
+    K.geometric_median_weights(L, slots, L.total, P, pair, w, iters_out=its)
+    torch.cuda.synchronize()
+    assert float(pair.abs().sum()) == 0                                   # scratch handed back zeroed
+    assert torch.allclose(w.sum(1), torch.ones(T, device=dev), atol=1e-5) and float(w.min()) >= 0
+    assert int(its.max()) < 256, its                                       # converged, not cut off
+    sl = slots.cpu().double().numpy()
+    wn = w.cpu().double().numpy()
+    for t, spec in enumerate(L.specs):
+        X = sl[:, spec.offset:spec.offset + spec.numel]
+        ref = oracle.geometric_median(X, eps=1e-12, max_iter=2000)
+        got = wn[t] @ X
+        assert np.abs(got - ref).max() < 1e-3 * max(1.0, np.abs(ref).max()), (t, np.abs(got - ref).max())
+    # all inputs identical -> uniform weights, no NaN
+    same = honest[None].repeat(P, 1).contiguous()
+    K.geometric_median_weights(L, same, L.total, P, pair, w)
+    torch.cuda.synchronize()
+    assert torch.allclose(w, torch.full_like(w, 1.0 / P))
+
+
 # ------------------------------------------------------------------------------------------------ cast / flags
 def test_cast_and_flag_kernels(K, dev):
     L = small_layout()
