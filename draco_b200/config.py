@@ -56,6 +56,8 @@ class JobConfig:
     augment: bool = False
     data_on_device: bool = False    # keep the dataset in HBM and gather batches on the device
     metrics_file: Optional[str] = None
+    debug_checksum: bool = False    # verify every pushed gradient: loopback re-encode vs what landed in the PS slot (eager mode)
+    profile_phases: bool = False    # CUDA-event timers per phase (fetch/comp/encode/comm/decode/update); disables CUDA graphs
     multicast: str = "auto"         # auto | on | off  (NVLS multimem.st broadcast)
     spin_timeout_s: float = 60.0
     num_classes: int = 10
@@ -118,6 +120,11 @@ def add_fit_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
     a("--no-cuda", action="store_true", default=False, help="run on CPU over the Gloo transport")
     a("--seed", type=int, default=d.seed)
     a("--log-interval", type=int, default=d.log_interval)
+    a("--debug-checksum", action="store_true", default=d.debug_checksum,
+      help="transport self-check: each worker re-encodes its gradient into a local buffer and the PS compares 64-bit "
+           "checksums with what arrived in its slots, every step (eager mode, nvl transport)")
+    a("--profile-phases", action="store_true", default=d.profile_phases,
+      help="time the reference's phases (Comm / Comp / Encode / Method / Update) with CUDA events each step; eager mode")
     a("--network", type=str, default=d.network)
     a("--mode", type=str, default=d.mode, help="normal | geometric_median | krum (baseline); normal | maj_vote (maj_vote)")
     a("--dataset", type=str, default=d.dataset)

@@ -25,6 +25,7 @@ from ..codes.adversary import generate_schedule
 from ..config import JobConfig
 from ..data import TensorDataset
 from ..utils.codec import compress, decompress
+from ..utils.metrics import PhaseTimer
 from .arena import ArenaLayout
 from .fused_engine import make_plan
 from .placement import Placement
@@ -67,6 +68,8 @@ class CollectiveEngine:
         self.compress_gpu = cfg.compress and self.device.type == "cuda"
         self.bytes_up = 0
         self.bytes_up_raw = 0
+        self.timer = PhaseTimer(self.device.type == "cuda") if cfg.profile_phases else None
+        self.last_phases: Dict[str, float] = {}
 
     # ------------------------------------------------------------------ phases
     def _broadcast_params(self) -> None:
@@ -213,27 +216,40 @@ class CollectiveEngine:
                     dist.send(torch.frombuffer(bytearray(m), dtype=torch.uint8), dst=0, group=self.group)
 
     # ------------------------------------------------------------------ the step
+    def _phase(self, name: str):
+        import contextlib
+        return self.timer.phase(name) if self.timer else contextlib.nullcontext()
+
     def train_step(self, stage: bool = True) -> None:
         step = self.step
-        self._broadcast_params()
+        with self._phase("t_fetch"):                      # reference: "Comm" on the worker (weights down)
+            self._broadcast_params()
         if self.local_workers:
             if stage and self.worker.dataset is not None:
                 self.worker.stage_batches(step)
             for w in self.local_workers:
-                self.worker.forward_backward(w, step)
-                self._encode(w, step)
-        self._exchange_gradients(step)
+                with self._phase("t_comp"):
+                    self.worker.forward_backward(w, step)
+                with self._phase("t_encode"):
+                    self._encode(w, step)
+        with self._phase("t_comm"):                       # gradients up
+            self._exchange_gradients(step)
         if self.is_ps:
             if self.use_adv and self.cfg.err_mode == "omniscient":
                 self._omniscient(step)
-            self.ps.step(self.slots)
+            with self._phase("t_decode"):                 # reference: "Method Time Cost"
+                grads = self.ps.aggregate(self.slots)
+            with self._phase("t_update"):                 # reference: "Update Time Cost"
+                self.ps.apply(grads)
+        if self.timer:
+            self.last_phases = self.timer.elapsed()
         self.step += 1
 
     def read_metrics(self) -> Dict[str, float]:
         if not self.local_workers:
-            return {}
+            return dict(self.last_phases)
         m = torch.stack([self.worker.metrics[w] for w in self.local_workers]).mean(0).tolist()
-        return {"loss": m[0], "prec1": m[1], "prec5": m[2]}
+        return {"loss": m[0], "prec1": m[1], "prec5": m[2], **self.last_phases}
 
     def synchronize(self) -> None:
         if self.device.type == "cuda":

@@ -34,6 +34,7 @@ from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset
 from ..ops import kernels as K
 from .arena import ArenaLayout
+from ..utils.metrics import PhaseTimer
 from .placement import Placement
 from .ps import FusedPS, build_codes
 from .symm import SymmContext
@@ -60,7 +61,14 @@ class FusedEngine:
         self.step = 1                                   # host mirror of the device step counter
         self.kernels_per_step = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self._use_graph = cfg.cuda_graphs and cfg.err_mode != "omniscient"
+        self._use_graph = (cfg.cuda_graphs and cfg.err_mode != "omniscient" and not cfg.profile_phases
+                           and not cfg.debug_checksum)
+        self.debug_checksum = cfg.debug_checksum
+        self._dbg_sums: Dict[int, torch.Tensor] = {}
+        self._dbg_ps_sums: Optional[torch.Tensor] = None
+        self.checksum_log: List[dict] = []
+        self.timer = PhaseTimer(True) if cfg.profile_phases else None
+        self.last_phases: Dict[str, float] = {}
         self._eager_steps = 0
         self.overlap_push = cfg.overlap_push and not self.cyclic
         # PS pipelining: decode + apply + broadcast each gradient bucket as soon as all workers pushed it
@@ -126,7 +134,35 @@ class FusedEngine:
             self.ps = FusedPS(cfg, self.layout, device, self.params_f32, self.grad_in, self.groups, self.code)
             self.dst_ptrs = [mapA[p].ptr for p in self.place.worker_procs() if p != 0]
             self.param_flag_ptrs = [mapA[p].ptr + D * 4 for p in self.place.active_procs()]
+        self._dbg_buf = (torch.zeros(D * self.esize // 4, dtype=torch.float32, device=device)
+                         if self.debug_checksum and self.local_workers else None)
         self._initial_broadcast()
+
+    # ------------------------------------------------------------------ transport self-check
+    def _dbg_loopback(self, w: int, g32, g16, push_kw) -> None:
+        """Re-run the worker's encode + adversary into a LOCAL buffer and keep its 64-bit checksum (sum of the 32-bit
+        words): what the PS must find in slot ``w`` if every peer store of the real push landed."""
+        K.push_encode(self.layout, g32, g16, self._dbg_buf.data_ptr(), flag=None, **push_kw)
+        self._dbg_sums[w] = self._dbg_buf.view(torch.int32).sum(dtype=torch.int64)
+
+    def _verify_checksums(self, step: int) -> None:
+        sums = torch.zeros(self.P, dtype=torch.int64, device=self.device)
+        have = torch.zeros(self.P, dtype=torch.int64, device=self.device)
+        for w, v in self._dbg_sums.items():
+            sums[w - 1] = v
+            have[w - 1] = 1
+        self._dbg_sums = {}
+        if self.nprocs > 1:
+            dist.all_reduce(sums, group=self.group)
+            dist.all_reduce(have, group=self.group)
+        if self.is_ps:
+            got = self._dbg_ps_sums.cpu()
+            exp, hv = sums.cpu(), have.cpu()
+            bad = [w + 1 for w in range(self.P) if hv[w] and int(got[w]) != int(exp[w])]
+            self.checksum_log.append({"step": step, "checked": int(hv.sum()), "bad": bad})
+            if bad:
+                raise RuntimeError(f"step {step}: gradient slot checksum mismatch for worker(s) {bad} -- a peer store was "
+                                   f"lost or reordered past its flag")
 
     # ------------------------------------------------------------------ setup helpers
     def _initial_broadcast(self) -> None:
@@ -163,9 +199,12 @@ class FusedEngine:
         if self.local_workers:
             wc = self.worker
             nvtx.range_push("draco/worker: fetch params + compute + encode/push")   # reference phases: Comm / Comp / Encode
-            K.wait_flags([self.params_ready_ptr], self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_worker); n += 1
-            if wc.bf16:
-                K.cast_params(L, wc.binder.params_f32, wc.binder.params_c); n += 1
+            with self._phase("t_fetch"):
+                K.wait_flags([self.params_ready_ptr], self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_worker); n += 1
+                if wc.bf16:
+                    K.cast_params(L, wc.binder.params_f32, wc.binder.params_c); n += 1
+            comp_phase = self._phase("t_comp_encode_push")         # the push overlaps the backward pass: one phase
+            comp_phase.__enter__()
             order = list(self.local_workers)
             if step_host is not None and cfg.err_mode == "omniscient":
                 # liars read the honest slots: on a shared stream the honest workers must be enqueued first
@@ -209,6 +248,10 @@ class FusedEngine:
                     assert state["done"] == nb, "a gradient bucket never became ready"
                     torch.cuda.current_stream().wait_stream(self.push_stream)      # join (also required by capture)
                     n += nb
+                    if self.debug_checksum:
+                        if wc.zero_copy:
+                            wc.upload_ptrs(w, wc.R - 1, 0, L.ntensors)
+                        self._dbg_loopback(w, g32, g16, push_kw)
                     continue
                 wc.forward_backward(w, step_host)
                 if wc.zero_copy and not lying_now:
@@ -234,9 +277,14 @@ class FusedEngine:
                 else:
                     K.push_encode(L, g32, g16, self.slot_ptr(w), flag=self.grad_flag_ptr(w), **push_kw)
                     n += 1
+                    if self.debug_checksum:
+                        self._dbg_loopback(w, g32, g16, push_kw)
         if self.local_workers:
+            comp_phase.__exit__(None, None, None)
             nvtx.range_pop()
         if self.is_ps:
+            ps_phase = self._phase("t_gather_decode_update_bcast")
+            ps_phase.__enter__()
             nvtx.range_push("draco/ps: gather + decode + update + broadcast")            # reference: Method / Update time
             base = self.flagsB.data_ptr()
             if self.pipeline_ps:
@@ -256,8 +304,15 @@ class FusedEngine:
                                           dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
         if self.is_ps:
             nvtx.range_pop()
+            ps_phase.__exit__(None, None, None)
+            if self.debug_checksum:      # every gradient flag of this step has been waited for on this stream
+                self._dbg_ps_sums = self.grad_in.view(torch.int32).view(self.P, -1).sum(1, dtype=torch.int64)
         K.step_add(self.step_dev, 1); n += 1
         return n
+
+    def _phase(self, name: str):
+        import contextlib
+        return self.timer.phase(name) if self.timer else contextlib.nullcontext()
 
     def _capture(self) -> None:
         """Capture this process's whole step once; replays then advance the device-side step counter themselves.
@@ -283,6 +338,8 @@ class FusedEngine:
         With CUDA graphs the first two steps run eagerly, the third call captures, and from then on a step is one
         graph replay (plus the input staging copies)."""
         if not self.active:
+            if self.debug_checksum and self.nprocs > 1:
+                self._verify_checksums(self.step)          # collective: idle processes take part too
             self.step += 1
             return
         if self._use_graph and self.graph is None and self._eager_steps >= 2:
@@ -294,6 +351,8 @@ class FusedEngine:
         else:
             self.kernels_per_step = self._enqueue_local_step(self.step)
             self._eager_steps += 1
+            if self.debug_checksum:
+                self._verify_checksums(self.step)
         self.step += 1
         if stage:
             # prefetch: gather the next step's batches on the CPU while the GPU runs this step; the H2D copies are
@@ -312,11 +371,12 @@ class FusedEngine:
         if not self.local_workers:
             torch.cuda.current_stream().synchronize()
             self._check_error()
-            return {}
+            return self.timer.elapsed() if self.timer else {}
         m = torch.stack([self.worker.metrics[w] for w in self.local_workers]).mean(0)
         vals = m.tolist()
         self._check_error()
-        return {"loss": vals[0], "prec1": vals[1], "prec5": vals[2]}
+        phases = self.timer.elapsed() if self.timer else {}
+        return {"loss": vals[0], "prec1": vals[1], "prec5": vals[2], **phases}
 
     def synchronize(self) -> None:
         torch.cuda.synchronize()

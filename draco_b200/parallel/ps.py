@@ -237,7 +237,9 @@ class TorchPS:
         return out
 
     def step(self, slots: torch.Tensor) -> None:
-        grads = self.aggregate(slots)
+        self.apply(self.aggregate(slots))
+
+    def apply(self, grads: List[torch.Tensor]) -> None:
         mode = {"mean": "normal", "vote": "maj_vote", "krum": "krum", "geomedian": "geometric_median", "cyclic": "cyclic"}[self.rule]
         self.optimizer.step(grads=grads, mode=mode)
 

@@ -102,11 +102,11 @@ class Trainer:
             t0 = time.perf_counter()
             m = self.train_step()
             dt = time.perf_counter() - t0
-            if m:
+            if m and "loss" in m:
                 last = m
                 self.logger.log(step, "worker", t_step=dt, **m)
             if self.is_ps:
-                self.logger.log(step, "ps", t_step=dt)
+                self.logger.log(step, "ps", t_step=dt, **{k: v for k, v in (m or {}).items() if k.startswith("t_")})
             if step % cfg.eval_freq == 0:
                 self.checkpoint_and_eval(step)
         return last

@@ -28,14 +28,16 @@ class MetricsLogger:
             self._fh.write(json.dumps(rec) + "\n")
             self._fh.flush()
         if not self.quiet and step % self.log_interval == 0:
+            f = fields.get
             if role == "worker":
-                print("Worker: {}, Step: {}, Loss: {:.4f}, Time Cost: {:.4f}, Comp: {:.4f}, Comm: {:.4f}, Prec@1: {:.2f}, "
-                      "Prec@5: {:.2f}".format(self.rank, step, fields.get("loss", float("nan")), fields.get("t_step", 0.0),
-                                              fields.get("t_comp", 0.0), fields.get("t_comm", 0.0),
-                                              fields.get("prec1", float("nan")), fields.get("prec5", float("nan"))), flush=True)
+                comp = f("t_comp", f("t_comp_encode_push", 0.0))
+                print("Worker: {}, Step: {}, Loss: {:.4f}, Time Cost: {:.4f}, Comp: {:.4f}, Comm: {:.4f}, Encode: {:.4f}, "
+                      "Prec@1: {:.2f}, Prec@5: {:.2f}".format(self.rank, step, f("loss", float("nan")), f("t_step", 0.0), comp,
+                                                              f("t_fetch", 0.0) + f("t_comm", 0.0), f("t_encode", 0.0),
+                                                              f("prec1", float("nan")), f("prec5", float("nan"))), flush=True)
             else:
                 print("Master Step: {}, Method Time Cost: {:.6f}, Update Time Cost: {:.6f}".format(
-                    step, fields.get("t_decode", 0.0), fields.get("t_update", 0.0)), flush=True)
+                    step, f("t_decode", f("t_gather_decode_update_bcast", 0.0)), f("t_update", 0.0)), flush=True)
 
     def close(self) -> None:
         if self._fh:

@@ -130,3 +130,32 @@ def test_resnet50_bottlenecks_train_on_the_fused_path():
     assert all(l == l for l in losses)
     clean, _ = _run(_cfg(**dict(kw, worker_fail=0, err_mode="none")), 4)
     assert torch.equal(t.engine.master_params(), clean.engine.master_params())      # 2 liars of 5 are out-voted, bitwise
+
+
+@pytest.mark.parametrize("kw", [dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=2, err_mode="random"),
+                                dict(approach="cyclic", worker_fail=1, err_mode="constant"),
+                                dict(approach="baseline", mode="geometric_median", worker_fail=2, err_mode="rev_grad")])
+def test_debug_checksum_verifies_every_pushed_gradient(kw):
+    """--debug-checksum: loopback re-encode on the worker vs the words that landed in the PS slot."""
+    t, losses = _run(_cfg(debug_checksum=True, **kw), 4)
+    log = t.engine.checksum_log
+    assert [r["step"] for r in log] == [1, 2, 3, 4]
+    assert all(r["checked"] == 7 and r["bad"] == [] for r in log)
+    # a word flipped in a slot after the push must be caught
+    eng = t.engine
+    orig = eng._verify_checksums
+
+    def corrupt_then_verify(step):
+        eng._dbg_ps_sums = eng._dbg_ps_sums.clone()
+        eng._dbg_ps_sums[2] += 1
+        orig(step)
+
+    eng._verify_checksums = corrupt_then_verify
+    with pytest.raises(RuntimeError, match=r"checksum mismatch for worker\(s\) \[3\]"):
+        t.train_step()
+
+
+def test_profile_phases_on_the_fused_engine():
+    t, _ = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", profile_phases=True), 1)
+    m = t.train_step()
+    assert m["t_fetch"] >= 0 and m["t_comp_encode_push"] > 0 and m["t_gather_decode_update_bcast"] > 0

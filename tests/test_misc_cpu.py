@@ -63,3 +63,31 @@ def test_ops_fall_back_to_aten_on_cpu():
     assert {"conv1.weight", "bn1.running_mean", "layer1.0.conv1.weight", "layer2.0.shortcut.1.weight", "linear.bias"} <= keys
     vkeys = set(build_model("VGG11").state_dict())
     assert {"features.0.weight", "features.1.running_var", "features.4.weight", "classifier.1.weight", "classifier.6.bias"} <= vkeys
+
+
+def test_profile_phases_reports_reference_timers(tmp_path, capsys):
+    """--profile-phases: the reference's per-step timers (Comm / Comp / Encode on the worker, Method / Update on the PS)
+    land in the JSONL records and in the human lines."""
+    import json
+
+    import torch
+
+    from draco_b200 import JobConfig
+    from draco_b200.parallel.trainer import Trainer
+    mf = str(tmp_path / "m_{rank}.jsonl")
+    cfg = JobConfig(network="LeNet", dataset="MNIST", approach="maj_vote", mode="maj_vote", group_size=3, num_workers=3,
+                    worker_fail=1, err_mode="rev_grad", batch_size=16, max_steps=3, transport="gloo", synthetic_size=256,
+                    eval_freq=10 ** 6, profile_phases=True, metrics_file=mf, log_interval=1, train_dir=str(tmp_path) + "/")
+    t = Trainer(cfg, rank=0, world=1, device=torch.device("cpu"), quiet=False)
+    t.fit(3)
+    t.close()
+    recs = [json.loads(l) for l in open(mf.replace("{rank}", "0"))]
+    w = [r for r in recs if r["role"] == "worker"]
+    p = [r for r in recs if r["role"] == "ps"]
+    assert len(w) == 3 and len(p) == 3
+    for k in ("t_fetch", "t_comp", "t_encode", "t_comm"):
+        assert all(r[k] >= 0 for r in w), k
+    assert all(r["t_comp"] > 0 for r in w)
+    assert all(r["t_decode"] > 0 and r["t_update"] > 0 for r in p)
+    out = capsys.readouterr().out
+    assert "Comp:" in out and "Encode:" in out and "Method Time Cost" in out and "Update Time Cost" in out
