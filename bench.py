@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-overlap-push", action="store_true")
     ap.add_argument("--push-ctas", type=int, default=16)
     ap.add_argument("--no-pipeline-ps", action="store_true")
+    ap.add_argument("--worker-streams", type=int, default=None,
+                    help="concurrent CUDA streams for logical workers sharing a GPU (default: the JobConfig default)")
     return ap.parse_args()
 
 
@@ -80,7 +82,8 @@ def main() -> int:
                     lr=0.01, momentum=0.9, max_steps=total_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
                     cuda_graphs=not a.no_cuda_graphs and a.impl == "ours", compress_grad="None", multicast=a.multicast,
                     synthetic_size=8192, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas,
-                    pipeline_ps=not a.no_pipeline_ps)
+                    pipeline_ps=not a.no_pipeline_ps,
+                    **({"worker_streams": a.worker_streams} if a.worker_streams is not None else {}))
     trainer = Trainer(cfg, rank=rank, world=world, device=torch.device("cuda", local), quiet=True)
     eng = trainer.engine
     dev = torch.device("cuda", local)
@@ -190,7 +193,7 @@ def main() -> int:
                        "seq_len": None, "image": "3x32x32", "parallelism": f"ps1+w{a.num_workers} on {world} gpu",
                        "placement": eng.place.describe(), "code": f"repetition r={a.group_size} majority-vote" if a.approach == "maj_vote" else a.approach,
                        "adversaries_per_step": a.worker_fail, "err_mode": a.err_mode, "transport": transport,
-                       "cuda_graphs": bool(cfg.cuda_graphs), "nvls_multicast": bool(getattr(eng, "mc_params", None)),
+                       "cuda_graphs": bool(cfg.cuda_graphs), "worker_streams": len(getattr(eng, "worker_streams", []) or []) or 1, "nvls_multicast": bool(getattr(eng, "mc_params", None)),
                        "l2": "per-step working set (7x44.7 MB gradient slab + activations) exceeds the 126 MB L2; no explicit flush",
                        "images_per_s": value * a.batch_size * a.num_workers,
                        "note": ("adversaries are drawn over all workers each step like the reference (src/util.py:100-103), so "

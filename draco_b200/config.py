@@ -65,6 +65,7 @@ class JobConfig:
     overlap_push: bool = True       # ship gradient buckets while the remaining layers are still back-propagating
     pipeline_ps: bool = True        # PS votes / applies / broadcasts a bucket as soon as every worker pushed it
     push_ctas: int = 16             # CTAs of an overlapped bucket push (NVLink-bound: a handful of SMs saturates the link)
+    worker_streams: int = 1         # >1: logical workers sharing a GPU run on this many concurrent CUDA streams
     zero_copy_grads: bool = True    # push reads gradients where autograd left them (pointer table), no flat gather
 
     # ---- derived --------------------------------------------------------------------------
@@ -120,6 +121,9 @@ def add_fit_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
     a("--no-cuda", action="store_true", default=False, help="run on CPU over the Gloo transport")
     a("--seed", type=int, default=d.seed)
     a("--log-interval", type=int, default=d.log_interval)
+    a("--worker-streams", type=int, default=d.worker_streams,
+      help="logical workers that share one GPU are issued round-robin on this many CUDA streams (small layers of "
+           "different workers overlap); 1 = serial")
     a("--debug-checksum", action="store_true", default=d.debug_checksum,
       help="transport self-check: each worker re-encodes its gradient into a local buffer and the PS compares 64-bit "
            "checksums with what arrived in its slots, every step (eager mode, nvl transport)")

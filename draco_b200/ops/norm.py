@@ -39,14 +39,24 @@ def _lib():
     return lib
 
 
+# Set by the engine when logical workers run on concurrent streams: cooperative (grid-barrier) kernels need the whole GPU
+# to themselves, and only one worker per process may update the shared running statistics.
+FORCE_COOP: Optional[int] = None
+UPDATE_RUNNING_STATS = True
+
+
 def _counter(device: torch.device) -> torch.Tensor:
-    if device not in _counter_cache:
-        _counter_cache[device] = torch.zeros(16, dtype=torch.int32, device=device)
-    return _counter_cache[device]
+    """Grid-barrier / last-CTA counters; one set per (device, stream) so that concurrent streams never share them."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    if key not in _counter_cache:
+        _counter_cache[key] = torch.zeros(16, dtype=torch.int32, device=device)   # zero-filled on this very stream
+    return _counter_cache[key]
 
 
 def _coop() -> int:
     """1: single cooperative kernel per direction (statistics, grid barrier, apply); 0: two kernels."""
+    if FORCE_COOP is not None:
+        return FORCE_COOP
     return 0 if os.environ.get("DRACO_BN_COOP", "1") == "0" else 1
 
 
@@ -120,12 +130,17 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
         if (self.weight.dtype == torch.float32 and self.track_running_stats and fused_supported(x, self.training)
                 and (residual is None or residual.shape == x.shape)):
             backend_counters["fused"] += 1
-            if self.num_batches_tracked is not None:
+            upd = UPDATE_RUNNING_STATS
+            if upd and self.num_batches_tracked is not None:
                 self.num_batches_tracked.add_(1)
-            return _BnActFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+            return _BnActFn.apply(x, residual, self.weight, self.bias, self.running_mean if upd else None,
+                                  self.running_var if upd else None, self.eps,
                                   self.momentum if self.momentum is not None else 0.1, relu)
         backend_counters["aten"] += 1
-        y = super().forward(x)
+        if self.training and not UPDATE_RUNNING_STATS:
+            y = F.batch_norm(x, None, None, self.weight, self.bias, True, 0.0, self.eps)
+        else:
+            y = super().forward(x)
         if residual is not None:
             y = y + residual
         return F.relu(y) if relu else y

@@ -76,6 +76,12 @@ class FusedEngine:
         self.pipeline_ps = (self.overlap_push and cfg.pipeline_ps and select_rule(cfg) in ("mean", "vote")
                             and cfg.err_mode != "omniscient")
         self.push_stream = torch.cuda.Stream(device=device) if self.overlap_push else None
+        ns = min(max(int(cfg.worker_streams), 1), len(self.local_workers))
+        # (compute stream, push stream) pairs; omniscient liars need the serial order, phase timers one timeline
+        self.worker_streams = ([(torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)) for _ in range(ns)]
+                               if ns > 1 and cfg.err_mode != "omniscient" and not cfg.profile_phases and not cfg.debug_checksum
+                               else [])
+        self.push_counters = torch.zeros(cfg.num_workers + 1, dtype=torch.int32, device=device)
         self._staged_step = -1
 
         if cfg.deterministic:
@@ -209,76 +215,31 @@ class FusedEngine:
             if step_host is not None and cfg.err_mode == "omniscient":
                 # liars read the honest slots: on a shared stream the honest workers must be enqueued first
                 order.sort(key=lambda r: self.schedule.is_adversary(r, step_host))
-            for w in order:
-                g32 = [g[0] for g in wc.grads]
-                g16 = [g[1] for g in wc.grads]
-                coef = list(self.code.coeffs_of(w - 1)) if self.cyclic else None
-                lying_now = (step_host is not None and cfg.err_mode == "omniscient"
-                             and self.schedule.is_adversary(w, step_host))
-                push_kw = dict(step_ptr=self.step_dev, worker=w - 1, done_counter=self.counters[1:2], coef=coef,
-                               adv_bitmap=self.adv_bitmap, adv_len=len(self.schedule.ranks),
-                               attack=self.attack if self.attack != 4 else 0, magnitude=cfg.attack_magnitude, seed=cfg.seed,
-                               src_table=wc.ptr_dev[w] if wc.zero_copy else None)
-                if self.overlap_push and not lying_now:
-                    # bucketed push on a side stream, overlapped with the rest of the backward pass
-                    state = {"done": 0}
-                    nb = len(wc.buckets)
-
-                    def on_bucket(b, _w=w, _state=state, _g32=g32, _g16=g16, _kw=push_kw):
-                        t0, t1, idxs = wc.buckets[b]
-                        _state["done"] += 1
-                        if wc.zero_copy:                              # pointers of this bucket's gradients -> device table
-                            wc.upload_ptrs(_w, wc.R - 1, min(idxs), max(idxs) + 1)
-                        ev = torch.cuda.Event()
-                        ev.record()                                   # on the backward stream (autograd thread)
-                        with torch.cuda.stream(self.push_stream):
-                            self.push_stream.wait_event(ev)
-                            # few CTAs: the transfer is NVLink/ingress-bound and must not starve the backward kernels
-                            # it overlaps with (a full-GPU grid of store-stalled CTAs would hog every SM's warp slots)
-                            if self.pipeline_ps:
-                                flag = self.grad_flag_ptr(_w, b)                  # every bucket announces itself
-                            else:
-                                flag = self.grad_flag_ptr(_w) if _state["done"] == nb else None
-                            # remote slot: NVLink-bound, few CTAs; local slot (PS on this GPU): HBM-bound, 2 CTAs per SM
-                            grid = self.cfg.push_ctas if self.rank != 0 else 2 * K.sm_count()
-                            K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1), grid=min(grid, t1 - t0),
-                                          flag=flag, **_kw)
-
-                    wc.forward_backward(w, step_host, on_bucket=on_bucket)
-                    assert state["done"] == nb, "a gradient bucket never became ready"
-                    torch.cuda.current_stream().wait_stream(self.push_stream)      # join (also required by capture)
-                    n += nb
-                    if self.debug_checksum:
-                        if wc.zero_copy:
-                            wc.upload_ptrs(w, wc.R - 1, 0, L.ntensors)
-                        self._dbg_loopback(w, g32, g16, push_kw)
-                    continue
-                wc.forward_backward(w, step_host)
-                if wc.zero_copy and not lying_now:
-                    for k in range(wc.R):
-                        if k < wc.R - 1:
-                            # earlier sub-batches: their gradient tensors were detached from the parameters
-                            if not torch.cuda.is_current_stream_capturing():
-                                host = torch.tensor([g.data_ptr() for g in wc.grad_refs[w][k]], dtype=torch.int64).pin_memory()
-                                wc._pinned_keep.append(host)
-                                wc.ptr_dev[w][k].copy_(host, non_blocking=True)
-                        else:
-                            wc.upload_ptrs(w, k, 0, L.ntensors)
-                if lying_now:
-                    honest = 0
-                    for h in range(1, self.P + 1):
-                        if not self.schedule.is_adversary(h, step_host):
-                            honest |= 1 << (h - 1)
-                    flags = [self.grad_flag_ptr(h) for h in range(1, self.P + 1) if (honest >> (h - 1)) & 1]
-                    K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s)
-                    K.omniscient(self.ps_grad_base, L.total, honest, w - 1, cfg.attack_magnitude, L.total,
-                                 step_ptr=self.step_dev, done_counter=self.counters[1:2], flag=self.grad_flag_ptr(w))
-                    n += 2
-                else:
-                    K.push_encode(L, g32, g16, self.slot_ptr(w), flag=self.grad_flag_ptr(w), **push_kw)
-                    n += 1
-                    if self.debug_checksum:
-                        self._dbg_loopback(w, g32, g16, push_kw)
+            if self.worker_streams:
+                # Logical workers sharing this GPU are issued round-robin on concurrent streams: the late layers of a
+                # CIFAR ResNet launch 16-128 CTAs on 148 SMs, so kernels of different workers fill each other's gaps.
+                # Every worker's kernel sequence is unchanged => its gradient stays bit-identical to the serial run.
+                from ..ops import norm as _norm
+                main = torch.cuda.current_stream()
+                fork = torch.cuda.Event()
+                fork.record(main)
+                _norm.FORCE_COOP = 0
+                try:
+                    for i, w in enumerate(order):
+                        st, pst = self.worker_streams[i % len(self.worker_streams)]
+                        _norm.UPDATE_RUNNING_STATS = (i == 0)
+                        if i < len(self.worker_streams):
+                            st.wait_event(fork)
+                        with torch.cuda.stream(st):
+                            n += self._enqueue_worker(w, step_host, pst)
+                finally:
+                    _norm.FORCE_COOP = None
+                    _norm.UPDATE_RUNNING_STATS = True
+                for st, _ in self.worker_streams[: len(order)]:
+                    main.wait_stream(st)
+            else:
+                for w in order:
+                    n += self._enqueue_worker(w, step_host, self.push_stream)
         if self.local_workers:
             comp_phase.__exit__(None, None, None)
             nvtx.range_pop()
@@ -308,6 +269,81 @@ class FusedEngine:
             if self.debug_checksum:      # every gradient flag of this step has been waited for on this stream
                 self._dbg_ps_sums = self.grad_in.view(torch.int32).view(self.P, -1).sum(1, dtype=torch.int64)
         K.step_add(self.step_dev, 1); n += 1
+        return n
+
+    def _enqueue_worker(self, w: int, step_host: Optional[int], push_stream) -> int:
+        """Forward/backward + encode/push of logical worker ``w`` on the current stream (bucket pushes on ``push_stream``)."""
+        cfg, L, wc = self.cfg, self.layout, self.worker
+        n = 0
+        g32 = [g[0] for g in wc.grads]
+        g16 = [g[1] for g in wc.grads]
+        coef = list(self.code.coeffs_of(w - 1)) if self.cyclic else None
+        lying_now = (step_host is not None and cfg.err_mode == "omniscient"
+                     and self.schedule.is_adversary(w, step_host))
+        push_kw = dict(step_ptr=self.step_dev, worker=w - 1, done_counter=self.push_counters[w:w + 1], coef=coef,
+                       adv_bitmap=self.adv_bitmap, adv_len=len(self.schedule.ranks),
+                       attack=self.attack if self.attack != 4 else 0, magnitude=cfg.attack_magnitude, seed=cfg.seed,
+                       src_table=wc.ptr_dev[w] if wc.zero_copy else None)
+        if self.overlap_push and not lying_now:
+            # bucketed push on a side stream, overlapped with the rest of the backward pass
+            state = {"done": 0}
+            nb = len(wc.buckets)
+
+            def on_bucket(b, _w=w, _state=state, _g32=g32, _g16=g16, _kw=push_kw):
+                t0, t1, idxs = wc.buckets[b]
+                _state["done"] += 1
+                if wc.zero_copy:                              # pointers of this bucket's gradients -> device table
+                    wc.upload_ptrs(_w, wc.R - 1, min(idxs), max(idxs) + 1)
+                ev = torch.cuda.Event()
+                ev.record()                                   # on the backward stream (autograd thread)
+                with torch.cuda.stream(push_stream):
+                    push_stream.wait_event(ev)
+                    # few CTAs: the transfer is NVLink/ingress-bound and must not starve the backward kernels
+                    # it overlaps with (a full-GPU grid of store-stalled CTAs would hog every SM's warp slots)
+                    if self.pipeline_ps:
+                        flag = self.grad_flag_ptr(_w, b)                  # every bucket announces itself
+                    else:
+                        flag = self.grad_flag_ptr(_w) if _state["done"] == nb else None
+                    # remote slot: NVLink-bound, few CTAs; local slot (PS on this GPU): HBM-bound, 2 CTAs per SM
+                    grid = self.cfg.push_ctas if self.rank != 0 else 2 * K.sm_count()
+                    K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1), grid=min(grid, t1 - t0),
+                                  flag=flag, **_kw)
+
+            wc.forward_backward(w, step_host, on_bucket=on_bucket)
+            assert state["done"] == nb, "a gradient bucket never became ready"
+            torch.cuda.current_stream().wait_stream(push_stream)      # join (also required by capture)
+            n += nb
+            if self.debug_checksum:
+                if wc.zero_copy:
+                    wc.upload_ptrs(w, wc.R - 1, 0, L.ntensors)
+                self._dbg_loopback(w, g32, g16, push_kw)
+            return n
+        wc.forward_backward(w, step_host)
+        if wc.zero_copy and not lying_now:
+            for k in range(wc.R):
+                if k < wc.R - 1:
+                    # earlier sub-batches: their gradient tensors were detached from the parameters
+                    if not torch.cuda.is_current_stream_capturing():
+                        host = torch.tensor([g.data_ptr() for g in wc.grad_refs[w][k]], dtype=torch.int64).pin_memory()
+                        wc._pinned_keep.append(host)
+                        wc.ptr_dev[w][k].copy_(host, non_blocking=True)
+                else:
+                    wc.upload_ptrs(w, k, 0, L.ntensors)
+        if lying_now:
+            honest = 0
+            for h in range(1, self.P + 1):
+                if not self.schedule.is_adversary(h, step_host):
+                    honest |= 1 << (h - 1)
+            flags = [self.grad_flag_ptr(h) for h in range(1, self.P + 1) if (honest >> (h - 1)) & 1]
+            K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s)
+            K.omniscient(self.ps_grad_base, L.total, honest, w - 1, cfg.attack_magnitude, L.total,
+                         step_ptr=self.step_dev, done_counter=self.push_counters[w:w + 1], flag=self.grad_flag_ptr(w))
+            n += 2
+        else:
+            K.push_encode(L, g32, g16, self.slot_ptr(w), flag=self.grad_flag_ptr(w), **push_kw)
+            n += 1
+            if self.debug_checksum:
+                self._dbg_loopback(w, g32, g16, push_kw)
         return n
 
     def _phase(self, name: str):

@@ -159,3 +159,23 @@ def test_profile_phases_on_the_fused_engine():
     t, _ = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", profile_phases=True), 1)
     m = t.train_step()
     assert m["t_fetch"] >= 0 and m["t_comp_encode_push"] > 0 and m["t_gather_decode_update_bcast"] > 0
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_concurrent_worker_streams_are_bit_identical_to_serial(graphs):
+    """--worker-streams: logical workers sharing the GPU run on concurrent streams; every worker's kernel sequence is
+    unchanged, so parameters after K steps equal the serial run bit for bit (eager and under CUDA-graph replay)."""
+    kw = dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=2, err_mode="rev_grad", network="ResNet18",
+              dataset="Cifar10", batch_size=16, num_workers=7, dtype="bf16", synthetic_size=256, cuda_graphs=graphs)
+    a, la = _run(_cfg(worker_streams=1, **kw), 5)
+    b, lb = _run(_cfg(worker_streams=3, **kw), 5)
+    assert len(b.engine.worker_streams) == 3 and not a.engine.worker_streams
+    assert torch.equal(a.engine.master_params(), b.engine.master_params())
+    assert la == lb
+    D = b.engine.layout.total
+    slots = b.engine.grad_in.view(7, D)
+    groups = b.engine.groups.groups
+    for grp in groups:                                   # replicas of a group still agree exactly
+        honest = [w for w in grp if not b.engine.schedule.is_adversary(w, 5)]
+        for w in honest[1:]:
+            assert torch.equal(slots[honest[0] - 1], slots[w - 1])
