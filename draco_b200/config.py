@@ -65,7 +65,7 @@ class JobConfig:
     overlap_push: bool = True       # ship gradient buckets while the remaining layers are still back-propagating
     pipeline_ps: bool = True        # PS votes / applies / broadcasts a bucket as soon as every worker pushed it
     push_ctas: int = 16             # CTAs of an overlapped bucket push (NVLink-bound: a handful of SMs saturates the link)
-    worker_streams: int = 1         # >1: logical workers sharing a GPU run on this many concurrent CUDA streams
+    worker_streams: int = 4         # >1: logical workers sharing a GPU run on (up to) this many concurrent CUDA streams
     zero_copy_grads: bool = True    # push reads gradients where autograd left them (pointer table), no flat gather
 
     # ---- derived --------------------------------------------------------------------------

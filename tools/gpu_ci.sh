@@ -24,7 +24,7 @@ for s in $STAGES; do
     norm) timeout -k 10 300 python -m pytest tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/t_norm.log 2>&1; echo "norm rc=$?" ;;
     convbench) timeout -k 10 300 python tools/bench_conv.py > gpurun_out/conv_bench.log 2>&1; echo "convbench rc=$?" ;;
     ncu_conv) timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"conv3x3|wgrad_reduce" -s 8 -c 8 -f -o gpurun_out/prof_conv python tools/prof_conv.py > gpurun_out/ncu_conv.log 2>&1; echo "ncu_conv rc=$?" ;;
-    sanitizer) for tool in memcheck racecheck; do timeout -k 10 420 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider -x -k "push or vote or aggregate or geometric or krum or cyclic" > gpurun_out/sanitizer_$tool.log 2>&1; echo "sanitizer $tool rc=$?"; done ;;
+    sanitizer) for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do timeout -k 10 420 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider -x -k "push or vote or aggregate or geometric or krum or cyclic" > gpurun_out/sanitizer_$tool.log 2>&1; echo "sanitizer $tool rc=$?"; done ;;
     geomed) timeout -k 10 300 python -m pytest tests/test_kernels_gpu.py tests/test_fused_engine_gpu.py -q -m gpu -p no:cacheprovider -k "geomed or krum or geometric" > gpurun_out/t_geomed.log 2>&1; echo "geomed rc=$?"
             timeout -k 10 300 python bench.py --gpus 1 --steps 30 --warmup 5 --approach baseline --mode geometric_median > gpurun_out/bench1_geomed.log 2>&1; echo "bench geomed rc=$?" ;;
     alltests) timeout -k 10 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "alltests rc=$?" ;;
