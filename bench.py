@@ -127,20 +127,25 @@ def main() -> int:
     if not a.skip_e2e:
         cfg.data_on_device = False
         for _ in range(a.warmup):
-            trainer.train_step()
+            trainer.train_step_pipelined()
+        trainer.drain()
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         s.record()
         last = {}
+        # public API, pipelined result read: every step copies its inputs pinned-host -> device and its loss / Prec@k
+        # device -> host; the host looks at step k's numbers while step k+1 runs (Trainer.train_step_pipelined), and the
+        # last one is drained inside the timed region.
         for _ in range(a.steps):
-            last = trainer.train_step() or last
+            last = trainer.train_step_pipelined() or last
+        last = trainer.drain() or last
         e.record()
         barrier()
         wall = time.perf_counter() - t0
         e2e_ms = reduce_max(max(s.elapsed_time(e), wall * 1e3 if world == 1 else 0.0))
         h2d = reduce_sum(float(eng.worker.h2d_bytes if eng.local_workers else 0))
-        d2h = reduce_sum(12.0 if eng.local_workers else 0.0)
+        d2h = reduce_sum((12.0 if eng.local_workers else 0.0) + (4.0 if a.impl == "ours" else 0.0))   # loss/prec1/prec5 + watchdog word
         e2e = {"value": a.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "final_loss": mean_loss(last)}
 

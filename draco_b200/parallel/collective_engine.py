@@ -251,6 +251,13 @@ class CollectiveEngine:
         m = torch.stack([self.worker.metrics[w] for w in self.local_workers]).mean(0).tolist()
         return {"loss": m[0], "prec1": m[1], "prec5": m[2], **self.last_phases}
 
+    def enqueue_metrics_read(self):
+        """Same protocol as the fused engine's pipelined read; the library-op engine simply reads synchronously."""
+        return self.read_metrics()
+
+    def resolve_metrics(self, handle) -> Dict[str, float]:
+        return handle
+
     def synchronize(self) -> None:
         if self.device.type == "cuda":
             torch.cuda.synchronize()

@@ -414,6 +414,37 @@ class FusedEngine:
         phases = self.timer.elapsed() if self.timer else {}
         return {"loss": vals[0], "prec1": vals[1], "prec5": vals[2], **phases}
 
+    # Pipelined metric reads: the D2H copy of a step's loss / Prec@k (and of the watchdog word) is enqueued behind the
+    # step and resolved by the host one step later, so the next step's launch never waits for the previous step to drain.
+    def enqueue_metrics_read(self):
+        if self.timer is not None:                         # phase timers need the synchronous read
+            return self.read_metrics()
+        if not hasattr(self, "_mpin"):
+            self._mpin = [(torch.zeros(3, dtype=torch.float32).pin_memory(), torch.zeros(1, dtype=torch.int32).pin_memory(),
+                           torch.cuda.Event()) for _ in range(4)]
+            self._mslot = 0
+        slot = self._mslot
+        self._mslot = (slot + 1) % len(self._mpin)
+        pin_f, pin_e, ev = self._mpin[slot]
+        if self.local_workers:
+            m = torch.stack([self.worker.metrics[w] for w in self.local_workers]).mean(0)
+            pin_f.copy_(m, non_blocking=True)
+        pin_e.copy_(self.error, non_blocking=True)
+        ev.record()
+        return slot
+
+    def resolve_metrics(self, slot) -> Dict[str, float]:
+        if isinstance(slot, dict):
+            return slot
+        pin_f, pin_e, ev = self._mpin[slot]
+        ev.synchronize()
+        if int(pin_e[0]):
+            raise RuntimeError(f"rank {self.rank}: spin-wait watchdog fired (flag index {int(pin_e[0]) - 1}) -- a peer never arrived")
+        if not self.local_workers:
+            return {}
+        v = pin_f.tolist()
+        return {"loss": v[0], "prec1": v[1], "prec5": v[2]}
+
     def synchronize(self) -> None:
         torch.cuda.synchronize()
         self._check_error()

@@ -86,6 +86,20 @@ class Trainer:
         self.engine.train_step(stage=True)
         return self.engine.read_metrics()
 
+    def train_step_pipelined(self) -> Optional[Dict[str, float]]:
+        """One step through the public API with a *pipelined* result read: this step's inputs go pinned-host -> device,
+        the step is enqueued, the D2H copy of its loss / Prec@k is enqueued behind it, and the metrics of the PREVIOUS
+        step are returned (``None`` on the first call).  Every step's result is still read by the host -- one step late --
+        but the GPU never idles waiting for the host to look at a loss.  ``drain()`` returns the last one."""
+        self.engine.train_step(stage=True)
+        handle = self.engine.enqueue_metrics_read()
+        prev, self._pending = getattr(self, "_pending", None), (self.engine.step - 1, handle)
+        return self.engine.resolve_metrics(prev[1]) if prev is not None else None
+
+    def drain(self) -> Optional[Dict[str, float]]:
+        prev, self._pending = getattr(self, "_pending", None), None
+        return self.engine.resolve_metrics(prev[1]) if prev is not None else None
+
     def train_step_async(self, stage: bool = True) -> None:
         self.engine.train_step(stage=stage)
 
@@ -100,16 +114,26 @@ class Trainer:
         while self.engine.step <= end:
             step = self.engine.step
             t0 = time.perf_counter()
-            m = self.train_step()
+            prev = self.train_step_pipelined()              # metrics of step-1 (None right after a drain)
             dt = time.perf_counter() - t0
-            if m and "loss" in m:
-                last = m
-                self.logger.log(step, "worker", t_step=dt, **m)
-            if self.is_ps:
-                self.logger.log(step, "ps", t_step=dt, **{k: v for k, v in (m or {}).items() if k.startswith("t_")})
-            if step % cfg.eval_freq == 0:
-                self.checkpoint_and_eval(step)
+            if self._log_step(step - 1, prev, dt):
+                last = prev
+            if step % cfg.eval_freq == 0 or step == end:
+                cur = self.drain()                          # checkpoint / end of run: wait for the step just enqueued
+                if self._log_step(step, cur, dt):
+                    last = cur
+                if step % cfg.eval_freq == 0:
+                    self.checkpoint_and_eval(step)
         return last
+
+    def _log_step(self, step: int, m: Optional[Dict[str, float]], dt: float) -> bool:
+        if m is None:
+            return False
+        if "loss" in m:
+            self.logger.log(step, "worker", t_step=dt, **m)
+        if self.is_ps:
+            self.logger.log(step, "ps", t_step=dt, **{k: v for k, v in m.items() if k.startswith("t_")})
+        return "loss" in m
 
     # ------------------------------------------------------------------ eval / checkpoint
     def evaluate(self, max_batches: Optional[int] = None) -> Dict[str, float]:

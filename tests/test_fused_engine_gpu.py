@@ -179,3 +179,14 @@ def test_concurrent_worker_streams_are_bit_identical_to_serial(graphs):
         honest = [w for w in grp if not b.engine.schedule.is_adversary(w, 5)]
         for w in honest[1:]:
             assert torch.equal(slots[honest[0] - 1], slots[w - 1])
+
+
+def test_pipelined_metric_reads_return_the_same_numbers_one_step_late():
+    kw = dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", cuda_graphs=True)
+    _, sync_losses = _run(_cfg(**kw), 6)
+    t = Trainer(_cfg(**kw), rank=0, world=1, device=torch.device("cuda", 0), quiet=True)
+    got = [t.train_step_pipelined() for _ in range(6)]
+    assert got[0] is None
+    lag = [m["loss"] for m in got[1:]] + [t.drain()["loss"]]
+    assert lag == sync_losses
+    assert t.drain() is None
