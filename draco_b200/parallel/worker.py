@@ -109,9 +109,14 @@ class WorkerCompute:
         self.x_u8: Dict[int, List[torch.Tensor]] = {}
         self.y: Dict[int, List[torch.Tensor]] = {}
         self.metrics: Dict[int, torch.Tensor] = {}
-        for wk in local_workers:
-            self.x_u8[wk] = [torch.zeros(B, c, h, w, dtype=torch.uint8, device=self.device) for _ in range(self.R)]
-            self.y[wk] = [torch.zeros(B, dtype=torch.long, device=self.device) for _ in range(self.R)]
+        # all sub-batches of this process live in ONE device buffer (and one pinned host buffer): a step's inputs travel as
+        # a single H2D copy for the images and one for the labels instead of 2 per (worker, sub-batch)
+        nsub = max(len(local_workers) * self.R, 1)
+        self._x_all = torch.zeros(nsub, B, c, h, w, dtype=torch.uint8, device=self.device)
+        self._y_all = torch.zeros(nsub, B, dtype=torch.long, device=self.device)
+        for j, wk in enumerate(local_workers):
+            self.x_u8[wk] = [self._x_all[j * self.R + k] for k in range(self.R)]
+            self.y[wk] = [self._y_all[j * self.R + k] for k in range(self.R)]
             self.metrics[wk] = torch.zeros(3, dtype=torch.float32, device=self.device)   # loss, prec1, prec5
         self._pinned = None
         self._pin_slot = 0
@@ -156,14 +161,9 @@ class WorkerCompute:
                     torch.index_select(self.dataset.images, 0, tidx, out=px[i])
                 torch.index_select(self.dataset.labels, 0, tidx, out=py[i])
                 i += 1
-        nbytes = 0
-        i = 0
-        for wk in self.local_workers:
-            for k in range(self.R):
-                self.x_u8[wk][k].copy_(px[i], non_blocking=True)
-                self.y[wk][k].copy_(py[i], non_blocking=True)
-                nbytes += px[i].numel() + py[i].numel() * 8
-                i += 1
+        self._x_all.copy_(px, non_blocking=True)
+        self._y_all.copy_(py, non_blocking=True)
+        nbytes = px.numel() + py.numel() * 8
         if self.device.type == "cuda":
             ev = torch.cuda.Event()
             ev.record()
