@@ -34,7 +34,7 @@ from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset
 from ..ops import kernels as K
 from .arena import ArenaLayout
-from ..utils.metrics import PhaseTimer
+from ..utils.metrics import PhaseTimer, spin_wait
 from .placement import Placement
 from .ps import FusedPS, build_codes
 from .symm import SymmContext
@@ -403,16 +403,17 @@ class FusedEngine:
             raise RuntimeError(f"rank {self.rank}: spin-wait watchdog fired (flag index {e - 1}) -- a peer never arrived")
 
     def read_metrics(self) -> Dict[str, float]:
-        """Device -> host read of the step's loss / Prec@1 / Prec@5 (mean over local workers).  Synchronises."""
+        """Device -> host read of the step's loss / Prec@1 / Prec@5 (mean over local workers).  Waits for the step."""
+        if self.timer is None:
+            return self.resolve_metrics(self.enqueue_metrics_read())
         if not self.local_workers:
             torch.cuda.current_stream().synchronize()
             self._check_error()
-            return self.timer.elapsed() if self.timer else {}
+            return self.timer.elapsed()
         m = torch.stack([self.worker.metrics[w] for w in self.local_workers]).mean(0)
         vals = m.tolist()
         self._check_error()
-        phases = self.timer.elapsed() if self.timer else {}
-        return {"loss": vals[0], "prec1": vals[1], "prec5": vals[2], **phases}
+        return {"loss": vals[0], "prec1": vals[1], "prec5": vals[2], **self.timer.elapsed()}
 
     # Pipelined metric reads: the D2H copy of a step's loss / Prec@k (and of the watchdog word) is enqueued behind the
     # step and resolved by the host one step later, so the next step's launch never waits for the previous step to drain.
@@ -437,7 +438,7 @@ class FusedEngine:
         if isinstance(slot, dict):
             return slot
         pin_f, pin_e, ev = self._mpin[slot]
-        ev.synchronize()
+        spin_wait(ev)
         if int(pin_e[0]):
             raise RuntimeError(f"rank {self.rank}: spin-wait watchdog fired (flag index {int(pin_e[0]) - 1}) -- a peer never arrived")
         if not self.local_workers:

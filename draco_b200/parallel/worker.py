@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset, augment_cifar
 from ..models import build_model
+from ..utils.metrics import spin_wait
 from .arena import ArenaLayout, ModelBinder
 
 
@@ -148,7 +149,7 @@ class WorkerCompute:
         slot = self._pin_slot
         self._pin_slot ^= 1
         if self._pin_events[slot] is not None:
-            self._pin_events[slot].synchronize()
+            spin_wait(self._pin_events[slot])
         px, py = self._pinned[slot]
         i = 0
         for wk in self.local_workers:

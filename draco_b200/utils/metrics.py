@@ -17,6 +17,15 @@ from typing import Dict, List, Optional
 import torch
 
 
+def spin_wait(event) -> None:
+    """Wait for a CUDA event by polling ``cudaEventQuery``.  ``cudaEventSynchronize`` parks the thread in the driver's
+    blocking wait, whose wake-up was measured to arrive up to ~50 ms late on virtualised B200 boxes (a periodic stall every
+    few steps in the pipelined loop, `tools/diag_e2e.py`); a query loop returns within microseconds of completion.  The
+    waits this is used for are bounded by one training step."""
+    while not event.query():
+        pass
+
+
 class MetricsLogger:
     def __init__(self, path: Optional[str] = None, rank: int = 0, log_interval: int = 10, quiet: bool = False):
         self.rank, self.log_interval, self.quiet = rank, max(log_interval, 1), quiet

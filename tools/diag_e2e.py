@@ -47,6 +47,7 @@ wall = (T() - t_all) / 20 * 1e3
 import statistics as st
 names = ("replay", "stage(next)", "enqueue_metrics", "resolve(prev)")
 print("wall ms/step %.3f device ms/step %.3f" % (wall, s.elapsed_time(e) / 20))
+print("per-step total ms:", " ".join("%.1f" % (sum(r) * 1e3) for r in rows), "| engine step at loop start:", eng.step - 20)
 for j, n in enumerate(names):
     v = [r[j] * 1e3 for r in rows[2:]]
     print("  %-16s median %.3f max %.3f" % (n, st.median(v), max(v)))
