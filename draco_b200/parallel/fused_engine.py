@@ -34,7 +34,7 @@ from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset
 from ..ops import kernels as K
 from .arena import ArenaLayout
-from ..utils.metrics import PhaseTimer, spin_wait
+from ..utils.metrics import PhaseTimer, limit_host_threads, wait_event
 from .placement import Placement
 from .ps import FusedPS, build_codes
 from .symm import SymmContext
@@ -49,6 +49,7 @@ class FusedEngine:
     def __init__(self, cfg: JobConfig, rank: int, nprocs: int, device: torch.device, dataset: Optional[TensorDataset],
                  group=None):
         assert device.type == "cuda", "the nvl transport needs a GPU"
+        limit_host_threads()
         self.cfg, self.rank, self.nprocs, self.device, self.group = cfg, rank, nprocs, device, group
         self.place = Placement(cfg.num_workers, nprocs)
         self.P = cfg.num_workers
@@ -422,7 +423,7 @@ class FusedEngine:
             return self.read_metrics()
         if not hasattr(self, "_mpin"):
             self._mpin = [(torch.zeros(3, dtype=torch.float32).pin_memory(), torch.zeros(1, dtype=torch.int32).pin_memory(),
-                           torch.cuda.Event()) for _ in range(4)]
+                           torch.cuda.Event(blocking=True)) for _ in range(4)]
             self._mslot = 0
         slot = self._mslot
         self._mslot = (slot + 1) % len(self._mpin)
@@ -438,7 +439,7 @@ class FusedEngine:
         if isinstance(slot, dict):
             return slot
         pin_f, pin_e, ev = self._mpin[slot]
-        spin_wait(ev)
+        wait_event(ev)
         if int(pin_e[0]):
             raise RuntimeError(f"rank {self.rank}: spin-wait watchdog fired (flag index {int(pin_e[0]) - 1}) -- a peer never arrived")
         if not self.local_workers:

@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset, augment_cifar
 from ..models import build_model
-from ..utils.metrics import spin_wait
+from ..utils.metrics import wait_event
 from .arena import ArenaLayout, ModelBinder
 
 
@@ -149,7 +149,7 @@ class WorkerCompute:
         slot = self._pin_slot
         self._pin_slot ^= 1
         if self._pin_events[slot] is not None:
-            spin_wait(self._pin_events[slot])
+            wait_event(self._pin_events[slot])
         px, py = self._pinned[slot]
         i = 0
         for wk in self.local_workers:
@@ -166,7 +166,7 @@ class WorkerCompute:
         self._y_all.copy_(py, non_blocking=True)
         nbytes = px.numel() + py.numel() * 8
         if self.device.type == "cuda":
-            ev = torch.cuda.Event()
+            ev = self._pin_events[slot] or torch.cuda.Event(blocking=True)
             ev.record()
             self._pin_events[slot] = ev
         self.h2d_bytes = nbytes

@@ -17,13 +17,21 @@ from typing import Dict, List, Optional
 import torch
 
 
-def spin_wait(event) -> None:
-    """Wait for a CUDA event by polling ``cudaEventQuery``.  ``cudaEventSynchronize`` parks the thread in the driver's
-    blocking wait, whose wake-up was measured to arrive up to ~50 ms late on virtualised B200 boxes (a periodic stall every
-    few steps in the pipelined loop, `tools/diag_e2e.py`); a query loop returns within microseconds of completion.  The
-    waits this is used for are bounded by one training step."""
-    while not event.query():
-        pass
+def wait_event(event) -> None:
+    """Host wait for a CUDA event created with ``blocking=True`` (cudaEventBlockingSync): the thread sleeps instead of
+    spinning.  Measured on the B200 boxes (`tools/diag_e2e.py`): a host that burns CPU while the GPU works -- a spinning
+    sync plus idle OpenMP workers spinning after every `index_select` of the input staging -- runs into the container's
+    CPU quota and is descheduled for ~50 ms every ~100 ms, which idles the GPU in any loop that reads results per step."""
+    event.synchronize()
+
+
+def limit_host_threads() -> None:
+    """One process drives one GPU; its CPU work is the input gather (a few hundred KB per step).  Unless the user chose
+    otherwise (OMP_NUM_THREADS), keep intra-op parallelism at one thread so that no pool of spinning OpenMP workers eats
+    the CPU quota (torchrun does the same for multi-process launches)."""
+    import os
+    if "OMP_NUM_THREADS" not in os.environ:
+        torch.set_num_threads(1)
 
 
 class MetricsLogger:

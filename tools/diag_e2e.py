@@ -45,6 +45,11 @@ e.record()
 torch.cuda.synchronize()
 wall = (T() - t_all) / 20 * 1e3
 import statistics as st
+try:
+    print("cgroup cpu.max:", open("/sys/fs/cgroup/cpu.max").read().strip(), "| cpus:", len(os.sched_getaffinity(0)),
+          "| torch threads:", torch.get_num_threads())
+except OSError:
+    pass
 names = ("replay", "stage(next)", "enqueue_metrics", "resolve(prev)")
 print("wall ms/step %.3f device ms/step %.3f" % (wall, s.elapsed_time(e) / 20))
 print("per-step total ms:", " ".join("%.1f" % (sum(r) * 1e3) for r in rows), "| engine step at loop start:", eng.step - 20)
