@@ -25,7 +25,7 @@ from ..codes.adversary import generate_schedule
 from ..config import JobConfig
 from ..data import TensorDataset
 from ..utils.codec import compress, decompress
-from ..utils.metrics import PhaseTimer
+from ..utils.metrics import PhaseTimer, limit_host_threads
 from .arena import ArenaLayout
 from .fused_engine import make_plan
 from .placement import Placement
@@ -46,6 +46,8 @@ class CollectiveEngine:
         self.cyclic = cfg.approach == "cyclic"
         self.step = 1
         self.kernels_per_step = 0
+        if self.device.type == "cuda":
+            limit_host_threads()            # same host policy as the fused engine (fair baseline: no OpenMP spin pool)
         if cfg.deterministic and self.device.type == "cuda":
             torch.backends.cudnn.deterministic = True
             torch.backends.cudnn.benchmark = False
