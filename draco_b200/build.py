@@ -26,7 +26,7 @@ OBJ_DIR = ROOT / "build" / "obj"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-pthread"]
 
 
 def _nvcc() -> str:

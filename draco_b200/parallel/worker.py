@@ -12,6 +12,7 @@ share the model, its parameter arena and the gradient arenas, and differ only in
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -140,6 +141,21 @@ class WorkerCompute:
             self._pinned = [(torch.zeros((n,) + tuple(shape), dtype=torch.uint8, pin_memory=pin),
                              torch.zeros((n, shape[0]), dtype=torch.long, pin_memory=pin)) for _ in range(2)]
 
+    def _native_loader(self):
+        """The C++ gather/augment thread pool (csrc/host/dataload.cpp) when the dataset is an in-memory uint8 array."""
+        if getattr(self, "_loader", None) is None and not getattr(self, "_loader_failed", False):
+            try:
+                from ..data.loader import NativeLoader
+                d = self.dataset
+                if (os.environ.get("DRACO_NATIVE_LOADER", "1") != "0" and d.images.dtype == torch.uint8 and d.images.dim() == 4
+                        and d.images.is_contiguous() and d.labels.dtype == torch.int64 and d.labels.is_contiguous()):
+                    self._loader = NativeLoader(d.images, d.labels, threads=2)
+                else:
+                    self._loader_failed = True
+            except (OSError, RuntimeError, AttributeError):
+                self._loader_failed = True
+        return getattr(self, "_loader", None)
+
     def stage_batches(self, step: int) -> int:
         """Host -> device copy of every sub-batch this process needs at ``step``.  Returns bytes copied."""
         assert self.dataset is not None
@@ -151,17 +167,26 @@ class WorkerCompute:
         if self._pin_events[slot] is not None:
             wait_event(self._pin_events[slot])
         px, py = self._pinned[slot]
+        aug = self.cfg.augment and self.dataset.name == "Cifar10"
+        loader = self._native_loader()
         i = 0
         for wk in self.local_workers:
             ids = self.plan.batch_ids(step, wk)
             for k, idx in enumerate(self.plan.indices(step, wk)):
-                tidx = torch.from_numpy(np.ascontiguousarray(idx)).long()
-                if self.cfg.augment and self.dataset.name == "Cifar10":
-                    px[i].copy_(augment_cifar(self.dataset.images[tidx], self.cfg.seed * 7919 + step * 131 + ids[k]))
+                # identical pixels for every holder of this (step, batch): the augmentation seed depends on those only
+                seed = (self.cfg.seed * 7919 + step * 131 + ids[k]) if aug else None
+                if loader is not None:
+                    loader.submit(idx, px[i], py[i], seed=seed)      # C++ worker threads write the pinned staging memory
                 else:
-                    torch.index_select(self.dataset.images, 0, tidx, out=px[i])
-                torch.index_select(self.dataset.labels, 0, tidx, out=py[i])
+                    tidx = torch.from_numpy(np.ascontiguousarray(idx)).long()
+                    if aug:
+                        px[i].copy_(augment_cifar(self.dataset.images[tidx], seed))
+                    else:
+                        torch.index_select(self.dataset.images, 0, tidx, out=px[i])
+                    torch.index_select(self.dataset.labels, 0, tidx, out=py[i])
                 i += 1
+        if loader is not None:
+            loader.wait()
         self._x_all.copy_(px, non_blocking=True)
         self._y_all.copy_(py, non_blocking=True)
         nbytes = px.numel() + py.numel() * 8

@@ -91,3 +91,28 @@ def test_profile_phases_reports_reference_timers(tmp_path, capsys):
     assert all(r["t_decode"] > 0 and r["t_update"] > 0 for r in p)
     out = capsys.readouterr().out
     assert "Comp:" in out and "Encode:" in out and "Method Time Cost" in out and "Update Time Cost" in out
+
+
+def test_native_loader_staging_equals_python_staging(monkeypatch):
+    """stage_batches through the C++ thread pool (gather + CIFAR augmentation) feeds the very same pixels as the Python path."""
+    import torch
+
+    from draco_b200 import JobConfig
+    from draco_b200.parallel.trainer import Trainer
+
+    def run(native):
+        monkeypatch.setenv("DRACO_NATIVE_LOADER", "1" if native else "0")
+        cfg = JobConfig(network="VGG11", dataset="Cifar10", approach="maj_vote", mode="maj_vote", group_size=3, num_workers=3,
+                        worker_fail=0, err_mode="none", batch_size=4, max_steps=3, transport="gloo", synthetic_size=64,
+                        eval_freq=10 ** 6, augment=True, lr=0.01)
+        t = Trainer(cfg, rank=0, world=1, device=torch.device("cpu"), quiet=True)
+        losses = [t.train_step()["loss"] for _ in range(3)]
+        used = getattr(t.engine.worker, "_loader", None) is not None
+        x = t.engine.worker.x_u8[1][0].clone()
+        t.close()
+        return losses, used, x
+
+    l1, used1, x1 = run(True)
+    l0, used0, x0 = run(False)
+    assert used1 and not used0
+    assert torch.equal(x1, x0) and l1 == l0

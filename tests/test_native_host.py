@@ -83,3 +83,53 @@ def test_cuda_library_abi_matches_ctypes():
                  "TensorMeta", "HyperParams", "TileView", "FlagList", "ProjectArgs", "LocateArgs", "GeoMedArgs",
                  "GeoMedPrepArgs", "PairDistArgs", "KrumSelectArgs"):
         assert getattr(lib, "drc_sizeof_" + name)() == C.sizeof(getattr(N, name)), name
+
+
+# ------------------------------------------------------------------------------------------------ native input pipeline
+def test_native_gather_augment_matches_python_reference():
+    import torch
+
+    from draco_b200.data import augment_cifar
+    from draco_b200.data.loader import gather_augment
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (300, 3, 32, 32), dtype=torch.uint8, generator=g)
+    labels = torch.randint(0, 10, (300,), generator=g)
+    idx = np.random.RandomState(1).randint(0, 300, size=77)
+    out = torch.zeros(77, 3, 32, 32, dtype=torch.uint8)
+    lab = torch.zeros(77, dtype=torch.int64)
+    gather_augment(images, labels, idx, out, lab)                       # plain gather
+    assert torch.equal(out, images[torch.from_numpy(idx)]) and torch.equal(lab, labels[torch.from_numpy(idx)])
+    for seed in (1, 12345, 2 ** 31 + 5):
+        gather_augment(images, labels, idx, out, lab, seed=seed)        # reflect-pad-4 crop + flip, same draws as Python
+        ref = augment_cifar(images[torch.from_numpy(idx)], seed)
+        assert torch.equal(out, ref), seed
+    with pytest.raises(IndexError):
+        gather_augment(images, labels, np.array([0, 300]), out[:2], lab[:2])
+
+
+def test_native_loader_thread_pool_overlapping_jobs():
+    import torch
+
+    from draco_b200.data import augment_cifar
+    from draco_b200.data.loader import NativeLoader
+    g = torch.Generator().manual_seed(3)
+    images = torch.randint(0, 256, (512, 1, 28, 28), dtype=torch.uint8, generator=g)      # MNIST-shaped
+    labels = torch.randint(0, 10, (512,), generator=g)
+    ld = NativeLoader(images, labels, threads=3)
+    rs = np.random.RandomState(4)
+    jobs = []
+    for j in range(24):
+        idx = rs.randint(0, 512, size=64)
+        out = torch.zeros(64, 1, 28, 28, dtype=torch.uint8)
+        lab = torch.zeros(64, dtype=torch.int64)
+        seed = None if j % 3 == 0 else 100 + j
+        jobs.append((idx, out, lab, seed, ld.submit(idx, out, lab, seed=seed)))
+    ld.wait()
+    for idx, out, lab, seed, _ in jobs:
+        src = images[torch.from_numpy(idx)]
+        assert torch.equal(out, src if seed is None else augment_cifar(src, seed))
+        assert torch.equal(lab, labels[torch.from_numpy(idx)])
+    t = ld.submit(np.array([600]), torch.zeros(1, 1, 28, 28, dtype=torch.uint8), torch.zeros(1, dtype=torch.int64))
+    with pytest.raises(IndexError):
+        ld.wait(t)
+    ld.close()
