@@ -7,8 +7,8 @@ logging, ``--no-cuda`` forces the CPU/Gloo path) -- see DESIGN.md "flag semantic
 from __future__ import annotations
 
 import argparse
-from dataclasses import asdict, dataclass, field
-from typing import List, Optional
+from dataclasses import asdict, dataclass
+from typing import Optional
 
 APPROACHES = ("baseline", "maj_vote", "cyclic")
 MODES = ("normal", "geometric_median", "krum", "maj_vote")

@@ -18,7 +18,6 @@ from __future__ import annotations
 from typing import Callable, List, Optional
 
 import torch
-from torch import nn
 
 GradCallback = Callable[[int, torch.nn.Parameter], None]
 

@@ -7,7 +7,7 @@ library is missing the call raises (see ``_native.cuda``).
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Union
+from typing import Optional, Sequence, Union
 
 import torch
 

@@ -11,7 +11,6 @@ copy that a cast kernel refreshes from the fp32 arena the PS broadcasts.  The *w
 """
 from __future__ import annotations
 
-import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 

@@ -14,13 +14,11 @@ fp32 (complex64 for the cyclic code); ``--compress-grad compress`` runs the C++ 
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
-from .. import _native as N
 from ..codes.adversary import generate_schedule
 from ..config import JobConfig
 from ..data import TensorDataset

@@ -11,7 +11,6 @@ src/master/*.py):
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
