@@ -147,7 +147,10 @@ def main() -> int:
         h2d = reduce_sum(float(eng.worker.h2d_bytes if eng.local_workers else 0))
         d2h = reduce_sum((12.0 if eng.local_workers else 0.0) + (4.0 if a.impl == "ours" else 0.0))   # loss/prec1/prec5 + watchdog word
         e2e = {"value": a.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "final_loss": mean_loss(last)}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "final_loss": mean_loss(last),
+               "api": "Trainer.train_step_pipelined() + drain()",
+               "result_read": "every step's loss/Prec@k is copied device->host into pinned memory and read by the host one "
+                              "step later (while the next step runs); the last one is drained inside the timed region"}
 
     # ------------------------------------------------------------------ value: device-timed, no host sync in the loop
     cfg.data_on_device = True
