@@ -15,7 +15,9 @@ Step anatomy (one PS + P logical workers hosted by ``nprocs`` GPU processes; see
 
 There is no NCCL / MPI call and no host synchronisation anywhere in that loop; ordering between GPUs is carried by
 step-stamped, monotonically increasing flag words (acquire/release at system scope).  The whole per-process sequence is
-captured once in a CUDA graph and replayed; the step number lives in device memory so replays advance it.
+captured once in a CUDA graph and replayed; the step number lives in device memory so replays advance it.  Logical
+workers that share a GPU run on concurrent streams inside that graph (``--worker-streams``), their bucket pushes on side
+streams overlapped with the rest of the backward pass, and the PS consumes buckets as they complete (pipelined PS).
 
 Reference counterparts: master loops src/master/{baseline,rep,cyclic}_master.py ``start()``; worker loops
 src/worker/*_worker.py ``train()``; all mpi4py traffic listed in SURVEY.md section 2.3 "Collective / message call sites".
@@ -33,10 +35,10 @@ from ..codes.adversary import attack_code, generate_schedule
 from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset
 from ..ops import kernels as K
-from .arena import ArenaLayout
 from ..utils.metrics import PhaseTimer, limit_host_threads, wait_event
+from .arena import ArenaLayout
 from .placement import Placement
-from .ps import FusedPS, build_codes
+from .ps import FusedPS, build_codes, select_rule
 from .symm import SymmContext
 from .worker import WorkerCompute, make_model
 
@@ -69,11 +71,9 @@ class FusedEngine:
         self._dbg_ps_sums: Optional[torch.Tensor] = None
         self.checksum_log: List[dict] = []
         self.timer = PhaseTimer(True) if cfg.profile_phases else None
-        self.last_phases: Dict[str, float] = {}
         self._eager_steps = 0
         self.overlap_push = cfg.overlap_push and not self.cyclic
         # PS pipelining: decode + apply + broadcast each gradient bucket as soon as all workers pushed it
-        from .ps import select_rule
         self.pipeline_ps = (self.overlap_push and cfg.pipeline_ps and select_rule(cfg) in ("mean", "vote")
                             and cfg.err_mode != "omniscient")
         self.push_stream = torch.cuda.Stream(device=device) if self.overlap_push else None
