@@ -116,3 +116,36 @@ def test_native_loader_staging_equals_python_staging(monkeypatch):
     l0, used0, x0 = run(False)
     assert used1 and not used0
     assert torch.equal(x1, x0) and l1 == l0
+
+
+def test_load_dataset_reads_real_mnist_files_when_present(tmp_path):
+    """`load_dataset` prefers on-disk torchvision data (never downloads): feed it a miniature MNIST in the raw idx format."""
+    import struct
+
+    import numpy as np
+    import torch
+
+    from draco_b200.data import load_dataset
+    raw = tmp_path / "mnist_data" / "MNIST" / "raw"
+    raw.mkdir(parents=True)
+    rs = np.random.RandomState(0)
+
+    def write(prefix, n):
+        imgs = rs.randint(0, 256, size=(n, 28, 28), dtype=np.uint8)
+        labs = rs.randint(0, 10, size=(n,), dtype=np.uint8)
+        (raw / f"{prefix}-images-idx3-ubyte").write_bytes(struct.pack(">IIII", 2051, n, 28, 28) + imgs.tobytes())
+        (raw / f"{prefix}-labels-idx1-ubyte").write_bytes(struct.pack(">II", 2049, n) + labs.tobytes())
+        return imgs, labs
+
+    tr_i, tr_l = write("train", 64)
+    te_i, te_l = write("t10k", 16)
+    ds = load_dataset("MNIST", root=str(tmp_path), train=True)
+    assert not ds.synthetic and tuple(ds.images.shape) == (64, 1, 28, 28) and ds.images.dtype == torch.uint8
+    assert np.array_equal(ds.images[:, 0].numpy(), tr_i) and np.array_equal(ds.labels.numpy(), tr_l)
+    test = load_dataset("MNIST", root=str(tmp_path), train=False)
+    assert len(test) == 16 and np.array_equal(test.labels.numpy(), te_l)
+    x, y = ds.get_batch([3, 5, 7])
+    assert x.shape == (3, 1, 28, 28) and y.tolist() == tr_l[[3, 5, 7]].tolist()
+    # nothing on disk -> the synthetic stand-in of the same shape
+    syn = load_dataset("MNIST", root=str(tmp_path / "nowhere"), synthetic_size=128)
+    assert syn.synthetic and tuple(syn.images.shape) == (128, 1, 28, 28)
