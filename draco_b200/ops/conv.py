@@ -57,6 +57,16 @@ def _lib():
         lib.drc_conv3x3_wgrad_plan.restype = C.c_int
         lib.drc_conv3x3_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 7 + [N.ptr]
         lib.drc_conv3x3_wgrad.restype = C.c_int
+        lib.drc_convg_supported.argtypes = [C.c_int] * 6
+        lib.drc_convg_supported.restype = C.c_int
+        lib.drc_convg.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 8 + [N.ptr, N.ptr, C.c_int, C.c_int, N.ptr]
+        lib.drc_convg.restype = C.c_int
+        lib.drc_convg_wgrad_supported.argtypes = [C.c_int] * 6
+        lib.drc_convg_wgrad_supported.restype = C.c_int
+        lib.drc_convg_wgrad_plan.argtypes = [C.c_int] * 8 + [C.POINTER(C.c_longlong)]
+        lib.drc_convg_wgrad_plan.restype = C.c_int
+        lib.drc_convg_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 9 + [N.ptr]
+        lib.drc_convg_wgrad.restype = C.c_int
         lib._conv_ready = True
     return lib
 
@@ -99,6 +109,73 @@ def conv3x3_tcgen05(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False
     N.check(lib.drc_conv3x3(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, cin, cout, int(dgrad), bf32, bb16,
                             K.sm_count(act.device), act.device.index, torch.cuda.current_stream().cuda_stream), "conv3x3")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generalised tap-table kernels (csrc/cuda/conv_strided_tcgen05.cu): stride 1 or 2, 1x1 or 3x3.  EXPERIMENTAL -- compiled and
+# SASS-checked, not yet validated on hardware; opt-in with DRACO_CONV_STRIDED=tcgen05.
+# ---------------------------------------------------------------------------------------------------------------------
+def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, dgrad: bool = False,
+                  bias: torch.Tensor = None) -> torch.Tensor:
+    """``dgrad=False``: ``act`` = x [N, Cin, H, W] -> y [N, Cout, H/stride, W/stride];  ``dgrad=True``: ``act`` = dy -> dx.
+    ``in_hw`` is the spatial size of the forward input x; ``weight`` [Cout, Cin, ks, ks] in channels-last storage."""
+    from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
+    n = act.shape[0]
+    h, w = in_hw
+    cout, cin, ks = weight.shape[0], weight.shape[1], weight.shape[2]
+    assert act.is_contiguous(memory_format=torch.channels_last)
+    assert weight.permute(0, 2, 3, 1).is_contiguous(), "weights must be stored [Cout, ks, ks, Cin]"
+    oshape = (n, cin, h, w) if dgrad else (n, cout, h // stride, w // stride)
+    out = torch.empty(oshape, dtype=torch.bfloat16, device=act.device, memory_format=torch.channels_last)
+    bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
+    bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
+    N.check(lib.drc_convg(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, cin, cout, ks, stride, int(dgrad), bf32, bb16,
+                          K.sm_count(act.device), act.device.index, torch.cuda.current_stream().cuda_stream), "convg")
+    return out
+
+
+def convg_wgrad_tcgen05(dy: torch.Tensor, x: torch.Tensor, ks: int, stride: int) -> torch.Tensor:
+    """Weight gradient [Cout, Cin, ks, ks] (channels-last storage) of the strided / 1x1 / 3x3 convolution."""
+    import ctypes as C
+    from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
+    n, cout = dy.shape[0], dy.shape[1]
+    cin, h, w = x.shape[1], x.shape[2], x.shape[3]
+    assert dy.is_contiguous(memory_format=torch.channels_last) and x.is_contiguous(memory_format=torch.channels_last)
+    sms = K.sm_count(dy.device)
+    ws_elems = C.c_longlong(0)
+    lib.drc_convg_wgrad_plan(n, h, w, cin, cout, ks, stride, sms, C.byref(ws_elems))
+    ws = torch.empty(ws_elems.value, dtype=torch.float32, device=dy.device)
+    dw = torch.empty((cout, ks, ks, cin), dtype=torch.bfloat16, device=dy.device).permute(0, 3, 1, 2)   # [Cout,Cin,ks,ks] view
+    N.check(lib.drc_convg_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, w, cin, cout, ks, stride, sms,
+                                dy.device.index, torch.cuda.current_stream().cuda_stream), "convg_wgrad")
+    return dw
+
+
+class _ConvGFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride):
+        ctx.save_for_backward(x, weight)
+        ctx.stride, ctx.has_bias = stride, bias is not None
+        return convg_tcgen05(x, weight, x.shape[2:], stride, False, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = dw = db = None
+        backend_counters["tcgen05"] += 1
+        if ctx.needs_input_grad[0]:
+            dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True)
+        if ctx.needs_input_grad[1]:
+            dw = convg_wgrad_tcgen05(dy, x, weight.shape[2], ctx.stride)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum((0, 2, 3))
+        return dx, dw, db, None
 
 
 class _Conv3x3Fn(torch.autograd.Function):
@@ -155,7 +232,22 @@ class Conv2d(nn.Conv2d):
                 and os.environ.get("DRACO_CONV3X3", "cudnn") == "tcgen05"
                 and bool(_lib().drc_conv3x3_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, 0)))
 
+    def _strided_ok(self, x: torch.Tensor) -> bool:
+        """EXPERIMENTAL path (DRACO_CONV_STRIDED=tcgen05): stride-2 3x3 and 1x1 layers on the tap-table kernels."""
+        if os.environ.get("DRACO_CONV_STRIDED", "cudnn") != "tcgen05":
+            return False
+        ks = self.kernel_size[0]
+        return (self.kernel_size in ((1, 1), (3, 3)) and self.stride == (2, 2) and self.padding == (ks // 2, ks // 2)
+                and self.dilation == (1, 1) and self.groups == 1 and x.is_cuda and x.dtype == torch.bfloat16
+                and self.weight.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+                and self.weight.permute(0, 2, 3, 1).is_contiguous()
+                and bool(_lib().drc_convg_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, ks, 2))
+                and bool(_lib().drc_convg_wgrad_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, ks, 2)))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._strided_ok(x):
+            backend_counters["tcgen05"] += 1
+            return _ConvGFn.apply(x, self.weight, self.bias, 2)
         if self._conv3x3_ok(x):
             backend_counters["tcgen05"] += 1
             return _Conv3x3Fn.apply(x, self.weight, self.bias)

@@ -178,3 +178,58 @@ def test_conv3x3_layer_autograd_path(monkeypatch):
     y32 = F.conv2d(x32, w32, padding=1)
     y32.backward(gy.float())
     assert _rel_err(y, y32) < 1.5e-2 and _rel_err(x.grad, x32.grad) < 2e-2 and _rel_err(conv.weight.grad, w32.grad) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# EXPERIMENTAL tap-table kernels (strided / 1x1 / 3x3): compiled and SASS-checked only -- run with DRACO_EXPERIMENTAL=1
+# ---------------------------------------------------------------------------------------------------------------------
+import os as _os
+
+experimental = pytest.mark.skipif(_os.environ.get("DRACO_EXPERIMENTAL", "0") != "1",
+                                  reason="kernels not yet validated on hardware; set DRACO_EXPERIMENTAL=1")
+
+
+@experimental
+@pytest.mark.parametrize("n,cin,cout,hw,ks,stride", [(128, 64, 128, 32, 3, 2), (128, 128, 256, 16, 3, 2), (128, 256, 512, 8, 3, 2),
+                                                     (128, 64, 128, 32, 1, 2), (64, 128, 256, 16, 1, 2), (5, 256, 512, 8, 1, 2),
+                                                     (8, 64, 64, 32, 3, 1), (16, 128, 128, 16, 3, 1), (6, 64, 128, 16, 1, 1)])
+def test_convg_tap_table_kernels(n, cin, cout, hw, ks, stride):
+    from draco_b200.ops.conv import convg_tcgen05, convg_wgrad_tcgen05
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(n + cin + cout + hw + ks + stride)
+    pad = ks // 2
+    x = torch.randn(n, cin, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, ks, ks, device=dev) * 0.05).to(torch.bfloat16)
+    w = w.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)                 # [Cout, ks, ks, Cin] storage
+    b = torch.randn(cout, device=dev)
+    y = convg_tcgen05(x, w, (hw, hw), stride, False, b)
+    ref = F.conv2d(x.float(), w.float(), b, stride=stride, padding=pad)
+    assert y.shape == ref.shape and _rel_err(y, ref) < 1.5e-2, _rel_err(y, ref)
+    dy = torch.randn_like(ref).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dx = convg_tcgen05(dy, w, (hw, hw), stride, True)
+    dref = torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), stride=stride, padding=pad)
+    assert dx.shape == dref.shape and _rel_err(dx, dref) < 1.5e-2, _rel_err(dx, dref)
+    dw = convg_wgrad_tcgen05(dy, x, ks, stride)
+    wref = torch.nn.grad.conv2d_weight(x.float(), (cout, cin, ks, ks), dy.float(), stride=stride, padding=pad)
+    assert dw.shape == wref.shape and _rel_err(dw, wref) < 1.5e-2, _rel_err(dw, wref)
+    assert torch.equal(convg_tcgen05(x, w, (hw, hw), stride, False, b), y)
+
+
+@experimental
+def test_convg_layer_autograd_path(monkeypatch):
+    from draco_b200.ops.conv import Conv2d, backend_counters
+    monkeypatch.setenv("DRACO_CONV_STRIDED", "tcgen05")
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(9)
+    for ks in (3, 1):
+        conv = Conv2d(64, 128, ks, stride=2, padding=ks // 2, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        x = torch.randn(16, 64, 32, 32, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        before = backend_counters["tcgen05"]
+        y = conv(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        assert backend_counters["tcgen05"] >= before + 2
+        x32, w32 = x.detach().float().requires_grad_(True), conv.weight.detach().float().requires_grad_(True)
+        y32 = F.conv2d(x32, w32, stride=2, padding=ks // 2)
+        y32.backward(gy.float())
+        assert _rel_err(y, y32) < 1.5e-2 and _rel_err(x.grad, x32.grad) < 2e-2 and _rel_err(conv.weight.grad, w32.grad) < 2e-2

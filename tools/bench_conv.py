@@ -42,5 +42,24 @@ for (n, c, k, hw) in [(128, 64, 64, 32), (128, 128, 128, 16), (128, 256, 256, 8)
     rows.append({"wgrad_us": t_w, "cudnn_wgrad_us": t_wc, "N": n, "Cin": c, "Cout": k, "HW": hw, "fprop_us": t_f, "cudnn_fprop_us": t_fc, "dgrad_us": t_d, "cudnn_dgrad_us": t_dc,
                  "fprop_tflops": fl / t_f / 1e6, "cudnn_fprop_tflops": fl / t_fc / 1e6})
     print(rows[-1], flush=True)
+if os.environ.get("DRACO_EXPERIMENTAL", "0") == "1":
+    # strided / 1x1 layers of ResNet-18 on the tap-table kernels vs cuDNN (the stride-2 dgrads are cuDNN's slowest kernels here)
+    from draco_b200.ops.conv import convg_tcgen05, convg_wgrad_tcgen05  # noqa: E402
+    for (n, c, k, hw, ks) in [(128, 64, 128, 32, 3), (128, 128, 256, 16, 3), (128, 256, 512, 8, 3), (128, 64, 128, 32, 1),
+                              (128, 128, 256, 16, 1), (128, 256, 512, 8, 1)]:
+        pad = ks // 2
+        x = torch.randn(n, c, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(k, c, ks, ks, device=dev) * 0.05).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        dy = torch.randn(n, k, hw // 2, hw // 2, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        args = (None, [2, 2], [pad, pad], [1, 1], False, [0, 0], 1)
+        row = {"N": n, "Cin": c, "Cout": k, "HW": hw, "ks": ks, "stride": 2,
+               "fprop_us": timeit(lambda: convg_tcgen05(x, w, (hw, hw), 2)),
+               "cudnn_fprop_us": timeit(lambda: F.conv2d(x, w, stride=2, padding=pad)),
+               "dgrad_us": timeit(lambda: convg_tcgen05(dy, w, (hw, hw), 2, True)),
+               "cudnn_dgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [True, False, False])),
+               "wgrad_us": timeit(lambda: convg_wgrad_tcgen05(dy, x, ks, 2)),
+               "cudnn_wgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [False, True, False]))}
+        rows.append(row)
+        print(row, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/conv_bench.json", "w"), indent=1)
