@@ -521,6 +521,28 @@ int encode_act(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int C, in
 
 }  // namespace
 
+// The tap table of one launch (also exported so that the host-side algebra can be tested without a GPU).
+//   fprop            : every filter tap (r, s); input pixel = output pixel * stride + (r - pad, s - pad)
+//   dgrad, class (ph, pw): output pixel (stride*i + ph, stride*j + pw) receives dy[i + dh, j + dw] * W[r, s] from the taps with
+//                      (ph + pad - r) and (pw + pad - s) divisible by the stride; dh = (ph + pad - r) / stride, dw likewise
+// Returns the number of taps; tap_index[t] = r * ks + s.
+extern "C" int drc_convg_taps(int ks, int stride, int dgrad, int ph, int pw, int* dh, int* dw, int* tap_index) {
+  const int pad = ks / 2;
+  int n = 0;
+  for (int rr = 0; rr < ks; ++rr) {
+    for (int ss = 0; ss < ks; ++ss) {
+      if (!dgrad) {
+        dh[n] = rr - pad; dw[n] = ss - pad;
+      } else {
+        if ((ph + pad - rr) % stride || (pw + pad - ss) % stride) continue;
+        dh[n] = (ph + pad - rr) / stride; dw[n] = (pw + pad - ss) / stride;
+      }
+      tap_index[n++] = rr * ks + ss;
+    }
+  }
+  return n;
+}
+
 // 1 if the forward geometry x[N,H,W,Cin] -> y[N,H/stride,W/stride,Cout] (ks x ks filter, pad ks/2) is served.
 extern "C" int drc_convg_supported(int H, int W, int Cin, int Cout, int ks, int stride) {
   if (!(ks == 1 || ks == 3) || !(stride == 1 || stride == 2)) return 0;
@@ -541,7 +563,7 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) return -2;
-  const int pad = ks / 2, OH = H / stride, OW = W / stride;
+  const int OH = H / stride, OW = W / stride;
   TapConvArgs a;
   a.N = N; a.OH = OH; a.OW = OW;                 // both passes iterate over an OH x OW grid per image (dgrad: per parity class)
   a.Cred = dgrad ? Cout : Cin; a.Cn = dgrad ? Cin : Cout;
@@ -563,8 +585,10 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   if (!dgrad) {
     int r = encode_act(enc, &tx, act, Cin, W, H, N, a.BW, a.BH, a.BN, stride);
     if (r) return 1000 + r;
-    a.in_mul = stride; a.ntaps = ks * ks;
-    for (int t = 0; t < a.ntaps; ++t) { a.tap_dh[t] = t / ks - pad; a.tap_dw[t] = t % ks - pad; a.tap_wcol[t] = t * Cin; }
+    int tidx[MAX_TAPS];
+    a.in_mul = stride;
+    a.ntaps = drc_convg_taps(ks, stride, 0, 0, 0, a.tap_dh, a.tap_dw, tidx);
+    for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
     a.out_H = OH; a.out_W = OW; a.out_mul = 1; a.out_oh = a.out_ow = 0;
     return block_n == 64 ? launch_g<64, false>(tx, tw, a, num_sms, stream) : launch_g<128, false>(tx, tw, a, num_sms, stream);
   }
@@ -581,19 +605,9 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   }
   for (int ph = 0; ph < stride; ++ph) {
     for (int pw = 0; pw < stride; ++pw) {
-      // output pixel (h, w) = (stride*i + ph, stride*j + pw) receives dy[(h + pad - r)/stride, (w + pad - s)/stride] * W[r, s]
-      // from the taps for which both numerators are multiples of the stride
-      a.ntaps = 0;
-      for (int rr = 0; rr < ks; ++rr) {
-        if ((ph + pad - rr) % stride) continue;
-        for (int ss = 0; ss < ks; ++ss) {
-          if ((pw + pad - ss) % stride) continue;
-          a.tap_dh[a.ntaps] = (ph + pad - rr) / stride;
-          a.tap_dw[a.ntaps] = (pw + pad - ss) / stride;
-          a.tap_wcol[a.ntaps] = (rr * ks + ss) * Cin;
-          ++a.ntaps;
-        }
-      }
+      int tidx[MAX_TAPS];
+      a.ntaps = drc_convg_taps(ks, stride, 1, ph, pw, a.tap_dh, a.tap_dw, tidx);
+      for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
       if (a.ntaps == 0) {
         // this parity class of dx receives nothing (1x1 / stride 2): it has to read as zero
         if (!zeroed) {

@@ -133,3 +133,67 @@ def test_native_loader_thread_pool_overlapping_jobs():
     with pytest.raises(IndexError):
         ld.wait(t)
     ld.close()
+
+
+# ------------------------------------------------------------------------------------------------ tap-table convolution algebra
+@pytest.mark.parametrize("ks,stride", [(3, 1), (3, 2), (1, 2), (1, 1)])
+def test_conv_tap_tables_reproduce_fprop_and_parity_class_dgrad(ks, stride):
+    """The host-side tables that drive the tap-table tcgen05 convolutions (csrc/cuda/conv_strided_tcgen05.cu), checked by
+    emulating the kernel's loads on the CPU: input pixel = patch origin * in_mul + tap offset (out-of-range reads as zero, as
+    the TMA unit fills), one weight column block per tap; strided dgrad assembled from its parity classes."""
+    import torch
+    import torch.nn.functional as F
+    if not N.cuda_available():
+        pytest.skip("libdraco_cuda.so not built")
+    lib = N.cuda()
+    lib.drc_convg_taps.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int)] * 3
+    lib.drc_convg_taps.restype = C.c_int
+
+    def taps(dgrad, ph=0, pw=0):
+        dh, dw, ti = (C.c_int * 9)(), (C.c_int * 9)(), (C.c_int * 9)()
+        n = lib.drc_convg_taps(ks, stride, int(dgrad), ph, pw, dh, dw, ti)
+        return [(dh[i], dw[i], ti[i]) for i in range(n)]
+
+    torch.manual_seed(ks * 10 + stride)
+    n, cin, cout, H = 2, 4, 5, 8
+    pad, OH = ks // 2, H // stride
+    x = torch.randn(n, H, H, cin, dtype=torch.float64)                       # NHWC like the kernels
+    w = torch.randn(cout, ks, ks, cin, dtype=torch.float64)                  # arena layout [Cout, ks, ks, Cin]
+    Wm = w.reshape(cout, ks * ks * cin)
+
+    def gather(t, i0, j0, mul, dh, dw):                                       # t[n, i*mul + dh, j*mul + dw, :] with zero fill
+        Hh = t.shape[1]
+        out = torch.zeros(n, len(i0), len(j0), t.shape[3], dtype=t.dtype)
+        for a_, i in enumerate(i0):
+            for b_, j in enumerate(j0):
+                hh, ww = i * mul + dh, j * mul + dw
+                if 0 <= hh < Hh and 0 <= ww < Hh:
+                    out[:, a_, b_] = t[:, hh, ww]
+        return out
+
+    # fprop
+    y = torch.zeros(n, OH, OH, cout, dtype=torch.float64)
+    tt = taps(False)
+    assert len(tt) == ks * ks
+    for dh, dw, ti in tt:
+        y += gather(x, range(OH), range(OH), stride, dh, dw) @ Wm[:, ti * cin:(ti + 1) * cin].t()
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert torch.allclose(y, ref, atol=1e-10)
+
+    # dgrad from parity classes (unit-stride reads of dy, stride-s writes of dx)
+    dy = torch.randn(n, OH, OH, cout, dtype=torch.float64)
+    dx = torch.zeros(n, H, H, cin, dtype=torch.float64)                       # (the launcher zero-fills when a class is empty)
+    total = 0
+    for ph in range(stride):
+        for pw in range(stride):
+            tt = taps(True, ph, pw)
+            total += len(tt)
+            acc = torch.zeros(n, OH, OH, cin, dtype=torch.float64)
+            for dh, dw, ti in tt:
+                acc += gather(dy, range(OH), range(OH), 1, dh, dw) @ Wm[:, ti * cin:(ti + 1) * cin]
+            if tt:
+                dx[:, ph::stride, pw::stride] = acc
+    assert total == ks * ks                                                   # every filter tap used exactly once overall
+    dref = torch.nn.grad.conv2d_input((n, cin, H, H), w.permute(0, 3, 1, 2), dy.permute(0, 3, 1, 2), stride=stride,
+                                      padding=pad).permute(0, 2, 3, 1)
+    assert torch.allclose(dx, dref, atol=1e-10)
