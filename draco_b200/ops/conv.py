@@ -67,6 +67,14 @@ def _lib():
         lib.drc_convg_wgrad_plan.restype = C.c_int
         lib.drc_convg_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 9 + [N.ptr]
         lib.drc_convg_wgrad.restype = C.c_int
+        lib.drc_conv_stem_supported.argtypes = [C.c_int] * 4
+        lib.drc_conv_stem_supported.restype = C.c_int
+        lib.drc_conv_stem_wgrad_parts.argtypes = [C.c_int] * 4
+        lib.drc_conv_stem_wgrad_parts.restype = C.c_int
+        lib.drc_conv_stem_fprop.argtypes = [N.ptr] * 4 + [C.c_int] * 4 + [N.ptr]
+        lib.drc_conv_stem_fprop.restype = C.c_int
+        lib.drc_conv_stem_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 5 + [N.ptr]
+        lib.drc_conv_stem_wgrad.restype = C.c_int
         lib._conv_ready = True
     return lib
 
@@ -153,6 +161,54 @@ def convg_wgrad_tcgen05(dy: torch.Tensor, x: torch.Tensor, ks: int, stride: int)
     N.check(lib.drc_convg_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, w, cin, cout, ks, stride, sms,
                                 dy.device.index, torch.cuda.current_stream().cuda_stream), "convg_wgrad")
     return dw
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3-channel stem (csrc/cuda/conv_stem.cu), CUDA cores.  EXPERIMENTAL -- opt-in with DRACO_CONV_STEM=native.
+# ---------------------------------------------------------------------------------------------------------------------
+def conv_stem_fprop(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:
+    """x: channels-last bf16 [N, 3, H, W]; weight [64, 3, 3, 3] stored [Cout, 3, 3, Cin] -> y channels-last [N, 64, H, W]."""
+    from .. import _native as N
+    n, _, h, w = x.shape
+    assert x.is_contiguous(memory_format=torch.channels_last) and weight.permute(0, 2, 3, 1).is_contiguous()
+    y = torch.empty((n, 64, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    b = bias.float().contiguous() if bias is not None else None
+    N.check(_lib().drc_conv_stem_fprop(x.data_ptr(), weight.data_ptr(), y.data_ptr(), b.data_ptr() if b is not None else None, n, h, w,
+                                       x.device.index, torch.cuda.current_stream().cuda_stream), "conv_stem_fprop")
+    return y
+
+
+def conv_stem_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
+    n, _, h, w = x.shape
+    assert dy.is_contiguous(memory_format=torch.channels_last) and x.is_contiguous(memory_format=torch.channels_last)
+    sms = K.sm_count(dy.device)
+    parts = lib.drc_conv_stem_wgrad_parts(n, h, w, sms)
+    ws = torch.empty(parts * 64 * 27, dtype=torch.float32, device=dy.device)
+    dw = torch.empty((64, 3, 3, 3), dtype=torch.bfloat16, device=dy.device).permute(0, 3, 1, 2)       # [Cout,Cin,3,3] view
+    N.check(lib.drc_conv_stem_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, w, sms, dy.device.index,
+                                    torch.cuda.current_stream().cuda_stream), "conv_stem_wgrad")
+    return dw
+
+
+class _ConvStemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x)
+        ctx.has_bias = bias is not None
+        return conv_stem_fprop(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        assert not ctx.needs_input_grad[0], "the stem kernel has no dgrad (network inputs carry no gradient)"
+        dw = conv_stem_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        db = dy.sum((0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return None, dw, db
 
 
 class _ConvGFn(torch.autograd.Function):
@@ -244,7 +300,18 @@ class Conv2d(nn.Conv2d):
                 and bool(_lib().drc_convg_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, ks, 2))
                 and bool(_lib().drc_convg_wgrad_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, ks, 2)))
 
+    def _stem_ok(self, x: torch.Tensor) -> bool:
+        return (os.environ.get("DRACO_CONV_STEM", "cudnn") == "native" and self.kernel_size == (3, 3) and self.stride == (1, 1)
+                and self.padding == (1, 1) and self.dilation == (1, 1) and self.groups == 1 and self.in_channels == 3
+                and self.out_channels == 64 and x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
+                and x.dim() == 4 and not x.requires_grad and x.is_contiguous(memory_format=torch.channels_last)
+                and self.weight.permute(0, 2, 3, 1).is_contiguous()
+                and bool(_lib().drc_conv_stem_supported(x.shape[2], x.shape[3], 3, 64)))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._stem_ok(x):
+            backend_counters["native_stem"] = backend_counters.get("native_stem", 0) + 1
+            return _ConvStemFn.apply(x, self.weight, self.bias)
         if self._strided_ok(x):
             backend_counters["tcgen05"] += 1
             return _ConvGFn.apply(x, self.weight, self.bias, 2)

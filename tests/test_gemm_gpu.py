@@ -233,3 +233,22 @@ def test_convg_layer_autograd_path(monkeypatch):
         y32 = F.conv2d(x32, w32, stride=2, padding=ks // 2)
         y32.backward(gy.float())
         assert _rel_err(y, y32) < 1.5e-2 and _rel_err(x.grad, x32.grad) < 2e-2 and _rel_err(conv.weight.grad, w32.grad) < 2e-2
+
+
+@experimental
+@pytest.mark.parametrize("n,hw", [(128, 32), (5, 32), (16, 16), (3, 64)])
+def test_conv_stem_native_kernels(n, hw):
+    from draco_b200.ops.conv import conv_stem_fprop, conv_stem_wgrad
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(n + hw)
+    x = torch.randn(n, 3, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 3, 3, 3, device=dev) * 0.2).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    b = torch.randn(64, device=dev)
+    y = conv_stem_fprop(x, w, b)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last) and _rel_err(y, ref) < 1e-2
+    dy = torch.randn(n, 64, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dw = conv_stem_wgrad(dy, x)
+    wref = torch.nn.grad.conv2d_weight(x.float(), (64, 3, 3, 3), dy.float(), padding=1)
+    assert dw.shape == wref.shape and _rel_err(dw, wref) < 1e-2, _rel_err(dw, wref)
+    assert torch.equal(conv_stem_wgrad(dy, x), dw)
