@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset, augment_cifar
 from ..models import build_model
+from ..ops import norm as _norm
 from ..utils.metrics import wait_event
 from .arena import ArenaLayout, ModelBinder
 
@@ -261,7 +262,8 @@ class WorkerCompute:
                 torch.manual_seed((self.cfg.seed * 1000003 + step_host * 8191 + ids[k]) & 0x7FFFFFFF)
             x = self._prep_input(self.x_u8[wk][k])
             y = self.y[wk][k]
-            out = self.model(x)
+            with _norm.deferred_batch_counts():             # one multi-tensor kernel for all num_batches_tracked bumps
+                out = self.model(x)
             loss = F.cross_entropy(out.float(), y)
             if on_bucket is not None and k == self.R - 1:
                 self._bucket_left = [len(idxs) for _, _, idxs in self.buckets]
