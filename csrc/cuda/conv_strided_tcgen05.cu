@@ -14,8 +14,9 @@
 // 9-tap instance of the same kernel.  Motivation (profiles/worker_profile_ResNet18_fused.txt): the three stride-2 dgrads
 // of ResNet-18 cost 220 us of a 2.0 ms step in cuDNN (93 us each for the two large ones) -- 5-10x their FLOP time.
 //
-// STATUS: compiles for sm_100a, SASS checked (UTCHMMA / UTMALDG); NOT yet validated on hardware -- opt-in via
-// DRACO_CONV_STRIDED=tcgen05, tests gated by DRACO_EXPERIMENTAL=1 (round-2 first item).
+// STATUS: numerics validated on a B200 (tests/test_gemm_gpu.py::test_convg_*: fprop / dgrad / wgrad for stride 1 and 2, 1x1 and
+// 3x3, plus the autograd path) at the very end of round 1; not yet timed against cuDNN, hence still opt-in via
+// DRACO_CONV_STRIDED=tcgen05 (round-2 first item: `bash tools/gpu_ci.sh experimental worker_native`).
 //
 // Reference counterpart: the strided nn.Conv2d layers of src/model_ops/resnet.py:14-64 (downsampling blocks + shortcuts).
 #include <cuda.h>

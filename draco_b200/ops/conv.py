@@ -120,8 +120,8 @@ def conv3x3_tcgen05(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# generalised tap-table kernels (csrc/cuda/conv_strided_tcgen05.cu): stride 1 or 2, 1x1 or 3x3.  EXPERIMENTAL -- compiled and
-# SASS-checked, not yet validated on hardware; opt-in with DRACO_CONV_STRIDED=tcgen05.
+# generalised tap-table kernels (csrc/cuda/conv_strided_tcgen05.cu): stride 1 or 2, 1x1 or 3x3.  Numerics validated on
+# hardware, not yet timed against cuDNN: opt-in with DRACO_CONV_STRIDED=tcgen05.
 # ---------------------------------------------------------------------------------------------------------------------
 def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, dgrad: bool = False,
                   bias: torch.Tensor = None) -> torch.Tensor:
@@ -164,7 +164,7 @@ def convg_wgrad_tcgen05(dy: torch.Tensor, x: torch.Tensor, ks: int, stride: int)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# 3-channel stem (csrc/cuda/conv_stem.cu), CUDA cores.  EXPERIMENTAL -- opt-in with DRACO_CONV_STEM=native.
+# 3-channel stem (csrc/cuda/conv_stem.cu), CUDA cores.  Numerics validated on hardware, not yet timed: opt-in with DRACO_CONV_STEM=native.
 # ---------------------------------------------------------------------------------------------------------------------
 def conv_stem_fprop(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:
     """x: channels-last bf16 [N, 3, H, W]; weight [64, 3, 3, 3] stored [Cout, 3, 3, Cin] -> y channels-last [N, 64, H, W]."""
@@ -289,7 +289,7 @@ class Conv2d(nn.Conv2d):
                 and bool(_lib().drc_conv3x3_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, 0)))
 
     def _strided_ok(self, x: torch.Tensor) -> bool:
-        """EXPERIMENTAL path (DRACO_CONV_STRIDED=tcgen05): stride-2 3x3 and 1x1 layers on the tap-table kernels."""
+        """Opt-in path (DRACO_CONV_STRIDED=tcgen05): stride-2 3x3 and 1x1 layers on the tap-table kernels."""
         if os.environ.get("DRACO_CONV_STRIDED", "cudnn") != "tcgen05":
             return False
         ks = self.kernel_size[0]
