@@ -23,16 +23,9 @@ from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset, augment_cifar
 from ..models import build_model
 from ..ops import norm as _norm
+from ..ops.loss import accuracy, cross_entropy_with_metrics  # noqa: F401  (accuracy re-exported)
 from ..utils.metrics import wait_event
 from .arena import ArenaLayout, ModelBinder
-
-
-def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1, 5)) -> List[torch.Tensor]:
-    """Prec@k in percent (the reference carries four copies of this helper, e.g. src/worker/utils.py:22-35)."""
-    maxk = min(max(topk), output.shape[1])
-    _, pred = output.float().topk(maxk, 1, True, True)
-    correct = pred.t().eq(target.view(1, -1))
-    return [correct[:min(k, maxk)].reshape(-1).float().sum() * (100.0 / target.shape[0]) for k in topk]
 
 
 def plan_buckets(layout: ArenaLayout, nbuckets: int = 5):
@@ -264,7 +257,7 @@ class WorkerCompute:
             y = self.y[wk][k]
             with _norm.deferred_batch_counts():             # one multi-tensor kernel for all num_batches_tracked bumps
                 out = self.model(x)
-            loss = F.cross_entropy(out.float(), y)
+            loss = cross_entropy_with_metrics(out, y, met, 1.0 / self.R)      # also accumulates loss / Prec@1 / Prec@5
             if on_bucket is not None and k == self.R - 1:
                 self._bucket_left = [len(idxs) for _, _, idxs in self.buckets]
                 self._bucket_cb = on_bucket
@@ -278,9 +271,6 @@ class WorkerCompute:
             if self.zero_copy:
                 self.grad_ptrs(0, self.layout.ntensors)          # validate dtype / strides against the arena layout
                 self.grad_refs[wk][k] = [p.grad for p in self.binder.params]
-            with torch.no_grad():
-                p1, p5 = accuracy(out.detach(), y)
-                met += torch.stack([loss.detach(), p1, p5]) / self.R
 
     # ------------------------------------------------------------------ zero-copy pointer tables
     def grad_ptrs(self, lo: int, hi: int) -> List[int]:

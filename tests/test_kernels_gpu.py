@@ -365,3 +365,38 @@ def test_cross_stream_flag_handshake(K, dev):
         K.push_encode(L, [g32], [None], dst, step_ptr=step, worker=0, done_counter=cnt[0:1], flag=flags[0:1])
     torch.cuda.synchronize()
     assert err.item() == 0 and torch.equal(out, g32)
+
+
+def test_fused_cross_entropy_kernel(monkeypatch):
+    """One-launch softmax-CE + gradient + Prec@k (csrc/cuda/loss_fused.cu) vs the PyTorch ops it replaces."""
+    import torch.nn.functional as F
+
+    from draco_b200.ops.loss import accuracy, cross_entropy_with_metrics
+    dev = torch.device("cuda", 0)
+    for (B, Cn, dt) in [(128, 10, torch.bfloat16), (37, 10, torch.float32), (64, 1000, torch.bfloat16), (5, 3, torch.float32)]:
+        torch.manual_seed(B + Cn)
+        logits = (torch.randn(B, Cn, device=dev) * 3).to(dt)
+        # spread the values so that no two logits of a row tie after rounding (topk's tie order is unspecified)
+        logits = (logits.float() + torch.arange(Cn, device=dev).float().view(1, -1) * 1e-2 * (1 if dt == torch.float32 else 8)).to(dt)
+        labels = torch.randint(0, Cn, (B,), device=dev)
+        met_ref = torch.zeros(3, device=dev)
+        monkeypatch.setenv("DRACO_FUSED_LOSS", "0")
+        l0 = logits.clone().requires_grad_(True)
+        loss0 = cross_entropy_with_metrics(l0, labels, met_ref, 0.5)
+        (loss0 * 2.0).backward()
+        monkeypatch.setenv("DRACO_FUSED_LOSS", "1")
+        met = torch.zeros(3, device=dev)
+        l1 = logits.clone().requires_grad_(True)
+        loss1 = cross_entropy_with_metrics(l1, labels, met, 0.5)
+        (loss1 * 2.0).backward()
+        assert abs(float(loss1) - float(loss0)) < 2e-3 * max(1.0, abs(float(loss0)))
+        tol = 2e-2 if dt == torch.bfloat16 else 1e-4
+        assert float((l1.grad.float() - l0.grad.float()).abs().max()) <= tol * float(l0.grad.float().abs().max())
+        assert torch.allclose(met, met_ref, rtol=2e-3, atol=1e-3), (met, met_ref)
+        # deterministic
+        met2 = torch.zeros(3, device=dev)
+        l2 = logits.clone().requires_grad_(True)
+        cross_entropy_with_metrics(l2, labels, met2, 0.5).backward()
+        l3 = logits.clone().requires_grad_(True)
+        cross_entropy_with_metrics(l3, labels, torch.zeros(3, device=dev), 0.5).backward()
+        assert torch.equal(l2.grad, l3.grad)
