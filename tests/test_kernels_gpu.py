@@ -367,6 +367,9 @@ def test_cross_stream_flag_handshake(K, dev):
     assert err.item() == 0 and torch.equal(out, g32)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("DRACO_EXPERIMENTAL", "0") != "1",
+                    reason="loss_fused.cu has not run on hardware yet (written after the round's GPU budget was spent); "
+                           "set DRACO_EXPERIMENTAL=1")
 def test_fused_cross_entropy_kernel(monkeypatch):
     """One-launch softmax-CE + gradient + Prec@k (csrc/cuda/loss_fused.cu) vs the PyTorch ops it replaces."""
     import torch.nn.functional as F
