@@ -212,12 +212,37 @@ class WorkerCompute:
 
     # ------------------------------------------------------------------ compute
     def _prep_input(self, x_u8: torch.Tensor) -> torch.Tensor:
+        if (os.environ.get("DRACO_FUSED_PREP", "0") == "1" and x_u8.is_cuda and x_u8.dim() == 4 and x_u8.shape[1] <= 4
+                and x_u8.is_contiguous() and self.channels_last):
+            return self._prep_input_fused(x_u8)
         x = (x_u8.float().div_(255.0).sub_(self._mean)).div_(self._std)
         if self.bf16:
             x = x.to(torch.bfloat16)
         if self.channels_last and x.dim() == 4:
             x = x.contiguous(memory_format=torch.channels_last)
         return x
+
+    def _prep_input_fused(self, x_u8: torch.Tensor) -> torch.Tensor:
+        """uint8 NCHW -> normalised channels-last tensor in the compute dtype, one launch (csrc/cuda/prep_input.cu)."""
+        import ctypes as C
+
+        from .. import _native as N
+        lib = N.cuda()
+        if not getattr(lib, "_prep_ready", False):
+            lib.drc_prep_input.argtypes = [N.ptr, N.ptr, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)] + [C.c_int] * 4 + [N.ptr]
+            lib.drc_prep_input.restype = C.c_int
+            lib._prep_ready = True
+        n, c, h, w = x_u8.shape
+        if getattr(self, "_prep_consts", None) is None:       # host copies of mean / std, read once (never under capture)
+            m = self._mean.flatten().float().cpu().tolist()
+            sd = self._std.flatten().float().cpu().tolist()
+            m, sd = (m * c)[:c] if len(m) == 1 else m, (sd * c)[:c] if len(sd) == 1 else sd
+            self._prep_consts = ((C.c_float * 4)(*(m + [0.0] * (4 - c))), (C.c_float * 4)(*(sd + [1.0] * (4 - c))))
+        dt = torch.bfloat16 if self.bf16 else torch.float32
+        out = torch.empty((n, c, h, w), dtype=dt, device=x_u8.device, memory_format=torch.channels_last)
+        N.check(lib.drc_prep_input(x_u8.data_ptr(), out.data_ptr(), int(self.bf16), self._prep_consts[0], self._prep_consts[1],
+                                   n, c, h, w, torch.cuda.current_stream().cuda_stream), "prep_input")
+        return out
 
     def _make_ready_hook(self, i: int):
         def hook(_param):

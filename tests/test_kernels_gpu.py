@@ -403,3 +403,26 @@ def test_fused_cross_entropy_kernel(monkeypatch):
         l3 = logits.clone().requires_grad_(True)
         cross_entropy_with_metrics(l3, labels, torch.zeros(3, device=dev), 0.5).backward()
         assert torch.equal(l2.grad, l3.grad)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DRACO_EXPERIMENTAL", "0") != "1",
+                    reason="prep_input.cu has not run on hardware yet; set DRACO_EXPERIMENTAL=1")
+def test_fused_input_prep_kernel(monkeypatch):
+    from draco_b200 import JobConfig
+    from draco_b200.data import synthetic_dataset
+    from draco_b200.parallel.fused_engine import make_plan
+    from draco_b200.parallel.ps import build_codes
+    from draco_b200.parallel.worker import WorkerCompute
+    dev = torch.device("cuda", 0)
+    for net, dsn in (("ResNet18", "Cifar10"), ("LeNet", "MNIST")):
+        cfg = JobConfig(network=net, dataset=dsn, approach="baseline", mode="normal", num_workers=1, batch_size=32, worker_fail=0,
+                        err_mode="none", transport="nvl", dtype="bf16", synthetic_size=64)
+        ds = synthetic_dataset(dsn, 64)
+        wc = WorkerCompute(cfg, dev, [1], make_plan(cfg, ds, build_codes(cfg)[0]), ds)
+        x = ds.images[:32].to(dev)
+        monkeypatch.setenv("DRACO_FUSED_PREP", "0")
+        ref = wc._prep_input(x)
+        monkeypatch.setenv("DRACO_FUSED_PREP", "1")
+        got = wc._prep_input(x)
+        assert got.shape == ref.shape and got.dtype == ref.dtype and got.stride() == ref.stride()
+        assert float((got.float() - ref.float()).abs().max()) <= 2e-2          # at most one bf16 ulp of a value ~2.6
