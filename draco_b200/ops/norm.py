@@ -35,8 +35,20 @@ def _lib():
         lib.drc_bn_fwd.restype = C.c_int
         lib.drc_bn_bwd.argtypes = [N.ptr] * 13 + [N.i64, C.c_int, C.c_int, C.c_int, C.c_int, st]
         lib.drc_bn_bwd.restype = C.c_int
+        lib.drc_bn_cluster_plan.argtypes = [N.i64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.drc_bn_cluster_plan.restype = C.c_int
+        lib.drc_bn_fwd_cluster.argtypes = [N.ptr] * 9 + [N.i64, C.c_int, C.c_float, C.c_float, C.c_int, st]
+        lib.drc_bn_fwd_cluster.restype = C.c_int
+        lib.drc_bn_bwd_cluster.argtypes = [N.ptr] * 10 + [N.i64, C.c_int, C.c_int, st]
+        lib.drc_bn_bwd_cluster.restype = C.c_int
         lib._bn_ready = True
     return lib
+
+
+def _cluster_path(M: int, c: int) -> bool:
+    """Single-launch cluster kernels (csrc/cuda/bn_cluster.cu) for tensors small enough to sit in one cluster's shared memory
+    per channel slice.  Opt-in (DRACO_BN_CLUSTER=1) until validated and timed on hardware."""
+    return os.environ.get("DRACO_BN_CLUSTER", "0") == "1" and bool(_lib().drc_bn_cluster_plan(M, c, None, None))
 
 
 # Set by the engine when logical workers run on concurrent streams: cooperative (grid-barrier) kernels need the whole GPU
@@ -108,13 +120,19 @@ class _BnActFn(torch.autograd.Function):
         y = torch.empty_like(x, memory_format=torch.channels_last)
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         invstd = torch.empty(c, dtype=torch.float32, device=dev)
-        ws = torch.empty(int(lib.drc_bn_workspace(M, c, _sms(dev))), dtype=torch.float32, device=dev)
         if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
             residual = residual.contiguous(memory_format=torch.channels_last)
-        N.check(lib.drc_bn_fwd(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
-                               _p(running_var), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), _counter(dev).data_ptr(),
-                               M, c, float(eps), float(momentum), int(relu), _sms(dev), _coop(),
-                               torch.cuda.current_stream().cuda_stream), "bn_fwd")
+        ctx.cluster = _cluster_path(M, c)
+        if ctx.cluster:
+            N.check(lib.drc_bn_fwd_cluster(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                           _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), M, c, float(eps),
+                                           float(momentum), int(relu), torch.cuda.current_stream().cuda_stream), "bn_fwd_cluster")
+        else:
+            ws = torch.empty(int(lib.drc_bn_workspace(M, c, _sms(dev))), dtype=torch.float32, device=dev)
+            N.check(lib.drc_bn_fwd(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
+                                   _p(running_var), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), _counter(dev).data_ptr(),
+                                   M, c, float(eps), float(momentum), int(relu), _sms(dev), _coop(),
+                                   torch.cuda.current_stream().cuda_stream), "bn_fwd")
         ctx.save_for_backward(x, y if relu else None, gamma, mean, invstd)
         ctx.relu, ctx.has_res = bool(relu), residual is not None
         return y
@@ -132,9 +150,14 @@ class _BnActFn(torch.autograd.Function):
         dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        torch.cuda.set_device(dev)
+        if getattr(ctx, "cluster", False):
+            N.check(lib.drc_bn_bwd_cluster(dy.data_ptr(), _p(y), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                           dx.data_ptr(), _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), M, c, int(ctx.relu),
+                                           torch.cuda.current_stream().cuda_stream), "bn_bwd_cluster")
+            return dx, dres, dgamma, dbeta, None, None, None, None, None
         sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
         ws = torch.empty(int(lib.drc_bn_workspace(M, c, _sms(dev))), dtype=torch.float32, device=dev)
-        torch.cuda.set_device(dev)
         N.check(lib.drc_bn_bwd(dy.data_ptr(), _p(y), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                dx.data_ptr(), _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), sums.data_ptr(),
                                _counter(dev)[8:].data_ptr(), M, c, int(ctx.relu), _sms(dev), _coop(),
