@@ -10,6 +10,8 @@ KEYS = [
     ("dram__bytes_write.sum", "dram wr"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
     ("lts__t_bytes.sum", "L2 bytes"),
+    ("lts__t_sectors_srcunit_tex_op_read.sum", "L2->SM rd sectors (x32 B)"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
     ("sm__inst_executed_pipe_tensor.sum", "tensor inst"),
