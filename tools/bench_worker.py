@@ -45,6 +45,6 @@ for mode in ("fused", "aten"):
         wc.forward_backward(1, None)
         torch.cuda.synchronize()
     tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90)
-    with open(os.path.join(out_dir, f"worker_profile_{net}_{mode}.txt"), "w") as fh:
+    with open(os.path.join(out_dir, f"worker_profile_{net}_{mode}{os.environ.get('PROFILE_TAG', '')}.txt"), "w") as fh:
         fh.write(f"{net} {mode}: {ms:.3f} ms per fwd+bwd (graph replay)\n\n" + tab)
     del wc, g
