@@ -128,7 +128,10 @@ def job_command(cfg: Cfg, job_args: List[str], node_rank: int, nnodes: int, npro
           f"--master-addr {master if nnodes > 1 else '127.0.0.1'} --master-port {cfg['master_port']} "
           f"-m draco_b200.cli.distributed_nn {' '.join(shlex.quote(a) for a in job_args)}")
     log = f"{cfg['remote_dir']}/job_node{node_rank}.log"
-    return f"cd {cfg['remote_dir']} && nohup {tr} > {log} 2>&1 & echo $!"
+    # setsid: the agent leads its own session / process group, so ``kill`` can address exactly that group by the recorded PID
+    # (the braces matter: only the agent is backgrounded, with all three standard streams redirected, so the launching shell --
+    # and the ssh / subprocess pipe behind it -- returns immediately with the PID instead of waiting for the job)
+    return f"cd {cfg['remote_dir']} && {{ setsid nohup {tr} > {log} 2>&1 < /dev/null & echo $!; }}"
 
 
 def run(cfg: Cfg, job_args: List[str], nnodes: int = 1, nproc: Optional[int] = None) -> Dict[str, int]:
@@ -163,7 +166,8 @@ def kill(cfg: Cfg) -> None:
     state = _state(cfg)
     for n, pid in state.get("pids", {}).items():
         if pid > 0:
-            run_on(cfg, n, f"kill -TERM -- -$(ps -o pgid= -p {pid} | tr -d ' ') 2>/dev/null || kill -TERM {pid} 2>/dev/null; true", 30)
+            # the recorded PID is a process-group leader (launched under setsid): signal that group, and only that group
+            run_on(cfg, n, f"kill -TERM -- -{pid} 2>/dev/null || kill -TERM {pid} 2>/dev/null; true", 30)
 
 
 def _state(cfg: Cfg) -> dict:

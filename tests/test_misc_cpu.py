@@ -149,3 +149,30 @@ def test_load_dataset_reads_real_mnist_files_when_present(tmp_path):
     # nothing on disk -> the synthetic stand-in of the same shape
     syn = load_dataset("MNIST", root=str(tmp_path / "nowhere"), synthetic_size=128)
     assert syn.synthetic and tuple(syn.images.shape) == (128, 1, 28, 28)
+
+
+def test_cluster_run_idle_kill_by_exact_process_group(tmp_path, monkeypatch):
+    """`cluster run` records the PID of every launched agent (its own session via setsid); `idle` polls exactly that PID and
+    `kill` signals exactly that process group -- never a name pattern (reference: ps-aux based idle detection / pkill)."""
+    import os
+    import time
+
+    from draco_b200.cli import cluster
+    cfg = cluster.load_cfg(None)
+    cfg.update({"nodes": ["localhost"], "remote_dir": str(tmp_path), "state_file": str(tmp_path / "state.json"), "gpus_per_node": 1})
+    monkeypatch.setattr(cluster, "job_command",
+                        lambda c, args, rank, nnodes, nproc: f"cd {c['remote_dir']} && {{ setsid nohup sleep 60 > job.log 2>&1 < /dev/null & echo $!; }}")
+    pids = cluster.run(cfg, ["--max-steps", "1"])
+    pid = pids["localhost"]
+    assert pid > 0 and os.path.exists(cfg["state_file"])
+    assert os.getpgid(pid) == pid and os.getpgid(pid) != os.getpgid(0)        # own group: killing it cannot touch the caller
+    assert cluster.idle(cfg) == {"localhost": False}
+    cluster.kill(cfg)
+    for _ in range(50):
+        if cluster.idle(cfg)["localhost"]:
+            break
+        time.sleep(0.1)
+    assert cluster.idle(cfg) == {"localhost": True}
+    monkeypatch.undo()
+    text = cluster.job_command(cfg, ["--network", "LeNet"], 0, 1, 8)
+    assert "setsid nohup" in text and "draco_b200.cli.distributed_nn --network LeNet" in text and text.rstrip().endswith("echo $!; }")
