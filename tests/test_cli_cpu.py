@@ -1,0 +1,59 @@
+"""End-to-end runs of the command-line entry points on CPU (subprocesses, like a user would launch them)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENV = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), OMP_NUM_THREADS="2")
+
+
+def _run(args, timeout=420, cwd=None):
+    r = subprocess.run([sys.executable, *args], capture_output=True, text=True, timeout=timeout, env=ENV, cwd=cwd or ROOT)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    return r.stdout + r.stderr
+
+
+def test_distributed_nn_single_process_then_evaluator(tmp_path):
+    """One process hosting the PS and every worker (the --no-cuda path), checkpoints every 2 steps, then the evaluator follows
+    the run through its checkpoints (reference: run_pytorch.sh + evaluate_pytorch.sh)."""
+    d = str(tmp_path) + "/"
+    out = _run(["-m", "draco_b200.cli.distributed_nn", "--no-cuda", "--network", "FC", "--dataset", "MNIST", "--approach", "cyclic",
+                "--worker-fail", "2", "--num-workers", "7", "--err-mode", "constant", "--batch-size", "4", "--lr", "0.01",
+                "--momentum", "0.9", "--max-steps", "4", "--eval-freq", "2", "--train-dir", d, "--compress-grad", "compress",
+                "--synthetic-size", "256", "--log-interval", "1"])
+    assert "I am master" in out and "Worker:" in out and "Master Step" in out
+    assert os.path.exists(d + "model_step_2") and os.path.exists(d + "model_step_4")
+    ev = _run(["-m", "draco_b200.cli.distributed_evaluator", "--network", "FC", "--dataset", "MNIST", "--model-dir", d, "--eval-freq", "2",
+               "--eval-batch-size", "64", "--device", "cpu", "--poll-s", "0.05", "--max-evals", "2", "--timeout-s", "20"])
+    assert ev.count("Prec@1") >= 2, ev[-1500:]
+
+
+def test_distributed_nn_launch_spawns_one_process_per_role(tmp_path):
+    """--launch 3: 1 PS + 2 workers as three Gloo processes (the reference's `mpirun -n 3`), resumed from a checkpoint once."""
+    d = str(tmp_path) + "/"
+    common = ["-m", "draco_b200.cli.distributed_nn", "--launch", "3", "--master-port", "29641", "--no-cuda", "--network", "LeNet",
+              "--dataset", "MNIST", "--approach", "maj_vote", "--mode", "maj_vote", "--group-size", "2", "--worker-fail", "0",
+              "--err-mode", "rev_grad", "--batch-size", "8", "--eval-freq", "3", "--train-dir", d, "--synthetic-size", "128",
+              "--compress-grad", "None", "--log-interval", "1"]
+    out = _run(common + ["--max-steps", "3"])
+    assert out.count("I am worker") == 2 and out.count("I am master") == 1
+    assert os.path.exists(d + "model_step_3")
+    out2 = _run(common + ["--max-steps", "5", "--checkpoint-step", "3"])
+    assert "Step: 4" in out2 and "Step: 5" in out2 and "Step: 2," not in out2            # continued after the checkpoint
+
+
+def test_single_machine_trainer_cli():
+    out = _run(["-m", "draco_b200.cli.single_machine", "--network", "LeNet", "--dataset", "MNIST", "--max-steps", "3", "--batch-size",
+                "16"])
+    assert "Prec@1" in out or "loss" in out.lower()
+
+
+def test_data_prepare_and_cluster_show_cfg(tmp_path):
+    out = _run(["-m", "draco_b200.data.prepare", "--root", str(tmp_path), "--synthetic-size", "64"])
+    assert os.path.exists(tmp_path / "synthetic_MNIST.pt") and os.path.exists(tmp_path / "synthetic_Cifar10.pt"), out
+    cfg = _run(["-m", "draco_b200.cli.cluster", "show_cfg"])
+    assert "nodes" in cfg and "remote_dir" in cfg
+    hosts = _run(["-m", "draco_b200.cli.cluster", "get_hosts"], cwd=str(tmp_path))
+    assert os.path.exists(tmp_path / "hosts_address"), hosts
