@@ -165,6 +165,10 @@ def test_cluster_run_idle_kill_by_exact_process_group(tmp_path, monkeypatch):
     pids = cluster.run(cfg, ["--max-steps", "1"])
     pid = pids["localhost"]
     assert pid > 0 and os.path.exists(cfg["state_file"])
+    for _ in range(100):                                                       # setsid() happens right after the fork
+        if os.getpgid(pid) == pid:
+            break
+        time.sleep(0.02)
     assert os.getpgid(pid) == pid and os.getpgid(pid) != os.getpgid(0)        # own group: killing it cannot touch the caller
     assert cluster.idle(cfg) == {"localhost": False}
     cluster.kill(cfg)
