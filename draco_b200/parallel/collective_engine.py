@@ -202,7 +202,10 @@ class CollectiveEngine:
                     payload = torch.empty(int(lens[i]), dtype=torch.uint8)
                     dist.recv(payload, src=src_proc, group=self.group)
                     arr = decompress(payload.numpy().tobytes())
-                    self.slots[w - 1, s.offset: s.offset + s.numel].copy_(torch.from_numpy(arr).view(self.slots.dtype))
+                    t = torch.from_numpy(arr)
+                    # cyclic codewords travel as [numel, 2] float32 (re, im) pairs
+                    t = torch.view_as_complex(t.reshape(-1, 2).contiguous()) if self.cyclic else t.reshape(-1)
+                    self.slots[w - 1, s.offset: s.offset + s.numel].copy_(t)
             elif src_proc == self.rank:
                 msgs = []
                 for s in L.specs:

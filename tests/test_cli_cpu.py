@@ -57,3 +57,18 @@ def test_data_prepare_and_cluster_show_cfg(tmp_path):
     assert "nodes" in cfg and "remote_dir" in cfg
     hosts = _run(["-m", "draco_b200.cli.cluster", "get_hosts"], cwd=str(tmp_path))
     assert os.path.exists(tmp_path / "hosts_address"), hosts
+
+
+def test_reference_example_job_scripts(tmp_path):
+    """tools/run_pytorch.sh is the reference's shipped example (src/run_pytorch.sh: FC/MNIST, cyclic code, n=7, s=2, constant
+    adversary, compression on); run it as 2 Gloo processes on CPU, then tools/evaluate_pytorch.sh on its checkpoint."""
+    env = dict(ENV, NPROC="2", MAX_STEPS="2", PORT="29671")
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "run_pytorch.sh"), "--no-cuda", "--synthetic-size", "128", "--eval-freq", "2"],
+                       capture_output=True, text=True, timeout=420, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    assert "I am master" in r.stdout and os.path.exists(tmp_path / "output" / "models" / "model_step_2")
+    env = dict(ENV, EVAL_FREQ="2")
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "evaluate_pytorch.sh"), "--device", "cpu", "--poll-s", "0.05", "--max-evals", "1",
+                        "--timeout-s", "20", "--eval-batch-size", "64"], capture_output=True, text=True, timeout=200, env=env,
+                       cwd=str(tmp_path))
+    assert r.returncode == 0 and "Prec@1" in r.stdout, (r.stdout[-1500:], r.stderr[-2000:])
