@@ -72,3 +72,20 @@ def test_reference_example_job_scripts(tmp_path):
                         "--timeout-s", "20", "--eval-batch-size", "64"], capture_output=True, text=True, timeout=200, env=env,
                        cwd=str(tmp_path))
     assert r.returncode == 0 and "Prec@1" in r.stdout, (r.stdout[-1500:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("name,flags", [
+    ("mean+codec", ["--approach", "baseline", "--mode", "normal", "--worker-fail", "0", "--compress-grad", "compress"]),
+    ("geomedian", ["--approach", "baseline", "--mode", "geometric_median", "--worker-fail", "1", "--err-mode", "rev_grad"]),
+    ("krum+async", ["--approach", "baseline", "--mode", "krum", "--worker-fail", "1", "--err-mode", "constant", "--comm-type", "Async"]),
+    ("cyclic", ["--approach", "cyclic", "--worker-fail", "1", "--err-mode", "random"]),
+    ("vote+omniscient", ["--approach", "maj_vote", "--mode", "maj_vote", "--group-size", "3", "--worker-fail", "1", "--err-mode",
+                         "omniscient"]),
+])
+def test_every_aggregation_rule_as_a_multi_process_job(tmp_path, name, flags):
+    """1 PS + 5 workers packed onto 2 Gloo processes, 3 steps, for every aggregation rule / wire option."""
+    port = 29700 + ["mean+codec", "geomedian", "krum+async", "cyclic", "vote+omniscient"].index(name)
+    out = _run(["-m", "draco_b200.cli.distributed_nn", "--launch", "2", "--master-port", str(port), "--no-cuda", "--network", "LeNet",
+                "--dataset", "MNIST", "--num-workers", "5", "--batch-size", "8", "--max-steps", "3", "--eval-freq", "1000",
+                "--train-dir", str(tmp_path) + "/", "--synthetic-size", "128", "--log-interval", "1", "--compress-grad", "None", *flags])
+    assert out.count("done at step 3") == 2, out[-2500:]
