@@ -149,6 +149,7 @@ class TorchPS:
         self.rule = select_rule(cfg)
         # flat per-tensor views in arena element order (the optimizer is element-wise, so order is irrelevant)
         views = [params[s.offset: s.offset + s.numel] for s in layout.specs]
+        self._views = views
         if cfg.optimizer == "adam":
             self.optimizer = AdamModified(views, lr=cfg.lr, weight_decay=cfg.weight_decay)
         else:
@@ -159,6 +160,25 @@ class TorchPS:
             f = (torch.randn(layout.total, generator=g) + 1.0) * torch.from_numpy(layout.valid_mask()).float()
             self.f = f.to(device)
         self.last_info: Dict[str, object] = {}
+
+    # --- optimizer state for checkpoints (the reference saves none: src/master/baseline_master.py:237-243) ----------
+    @property
+    def momentum(self) -> Optional[torch.Tensor]:
+        """SGD momentum buffers gathered into a flat arena (a copy), or None when there is nothing to save yet."""
+        from ..optim import SGDModified
+        if not isinstance(self.optimizer, SGDModified) or self.cfg.momentum == 0:
+            return None
+        arena, found = self.layout.new_arena(self.device), False
+        for v, spec in zip(self._views, self.layout.specs):
+            buf = self.optimizer.state.get(v, {}).get("momentum_buffer")
+            if buf is not None:
+                arena[spec.offset: spec.offset + spec.numel].copy_(buf)
+                found = True
+        return arena if found else None
+
+    def load_momentum(self, arena: torch.Tensor) -> None:
+        for v, spec in zip(self._views, self.layout.specs):
+            self.optimizer.state[v]["momentum_buffer"] = arena[spec.offset: spec.offset + spec.numel].clone()
 
     # --- per-tensor rules -----------------------------------------------------------------------
     def _vote_tensor(self, rows: List[torch.Tensor]) -> int:

@@ -166,8 +166,16 @@ class Trainer:
     def resume(self, step: int) -> None:
         blob = load_checkpoint(checkpoint_path(self.cfg.train_dir, step))
         eng = self.engine
-        mom = getattr(getattr(eng, "ps", None), "momentum", None)
-        restore_into(blob, eng.layout, eng.master_params(), mom if self.is_ps else None)
+        ps = getattr(eng, "ps", None)
+        if self.is_ps and hasattr(ps, "load_momentum"):
+            # library-op PS: the momentum lives in the optimizer's state, rebuild it from the checkpoint
+            arena = eng.layout.new_arena(eng.master_params().device) if blob.get("momentum") else None
+            restore_into(blob, eng.layout, eng.master_params(), arena)
+            if arena is not None:
+                ps.load_momentum(arena)
+        else:
+            mom = getattr(ps, "momentum", None)
+            restore_into(blob, eng.layout, eng.master_params(), mom if self.is_ps else None)
         if blob.get("buffers") and eng.worker is not None:
             eng.worker.model.load_state_dict(blob["buffers"], strict=False)
         eng.step = step + 1

@@ -124,6 +124,10 @@ def test_checkpoint_resume_and_evaluator(tmp_path):
     from draco_b200.utils.checkpoint import load_checkpoint
     blob = load_checkpoint(d + "model_step_3")
     assert blob["step"] == 3 and len(blob["state_dict"]) == 8 and blob["config"]["network"] == "LeNet"
+    assert blob["momentum"] is not None and set(blob["momentum"]) == set(blob["state_dict"])      # optimizer state is saved
+    for _ in range(3):
+        t2.train_step()
+    assert torch.equal(t2.engine.master_params(), final)       # steps 4-6 replayed bit for bit: parameters AND momentum restored
     from draco_b200.cli.distributed_evaluator import DistributedEvaluator
     ev = DistributedEvaluator("LeNet", "MNIST", d, eval_freq=3, eval_batch_size=128, device="cpu", poll_s=0.01)
     assert ev.evaluate(max_evals=2, timeout_s=1.0) == 2
