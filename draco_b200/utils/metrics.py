@@ -52,7 +52,7 @@ class MetricsLogger:
                       "Prec@1: {:.2f}, Prec@5: {:.2f}".format(self.rank, step, f("loss", float("nan")), f("t_step", 0.0), comp,
                                                               f("t_fetch", 0.0) + f("t_comm", 0.0), f("t_encode", 0.0),
                                                               f("prec1", float("nan")), f("prec5", float("nan"))), flush=True)
-            else:
+            elif role == "ps":
                 print("Master Step: {}, Method Time Cost: {:.6f}, Update Time Cost: {:.6f}".format(
                     step, f("t_decode", f("t_gather_decode_update_bcast", 0.0)), f("t_update", 0.0)), flush=True)
 
