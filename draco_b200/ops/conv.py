@@ -67,6 +67,10 @@ def _lib():
         lib.drc_convg_wgrad_plan.restype = C.c_int
         lib.drc_convg_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 9 + [N.ptr]
         lib.drc_convg_wgrad.restype = C.c_int
+        lib.drc_conv_halo_supported.argtypes = [C.c_int] * 4
+        lib.drc_conv_halo_supported.restype = C.c_int
+        lib.drc_conv_halo.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr, C.c_int, C.c_int, C.c_int, N.ptr]
+        lib.drc_conv_halo.restype = C.c_int
         lib.drc_conv_stem_supported.argtypes = [C.c_int] * 4
         lib.drc_conv_stem_supported.restype = C.c_int
         lib.drc_conv_stem_wgrad_parts.argtypes = [C.c_int] * 4
@@ -234,11 +238,33 @@ class _ConvGFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+def _halo_ok(h: int, w: int, cin: int, cout: int) -> bool:
+    """Halo-reuse kernels (csrc/cuda/conv_halo_tcgen05.cu) for the 64 -> 64 layers: opt-in with DRACO_CONV3X3=halo (never run
+    on hardware yet; DRACO_HALO_DESC=0|1 selects the descriptor base-offset convention to try)."""
+    return os.environ.get("DRACO_CONV3X3", "cudnn") == "halo" and bool(_lib().drc_conv_halo_supported(h, w, cin, cout))
+
+
+def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None) -> torch.Tensor:
+    from .. import _native as N
+    from . import kernels as K
+    n, _, h, w = act.shape
+    assert act.is_contiguous(memory_format=torch.channels_last) and weight.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((n, 64, h, w), dtype=torch.bfloat16, device=act.device, memory_format=torch.channels_last)
+    bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
+    bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
+    N.check(_lib().drc_conv_halo(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, int(dgrad), bf32, bb16,
+                                 int(os.environ.get("DRACO_HALO_DESC", "0")), K.sm_count(act.device), act.device.index,
+                                 torch.cuda.current_stream().cuda_stream), "conv_halo")
+    return out
+
+
 class _Conv3x3Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        if _halo_ok(x.shape[2], x.shape[3], weight.shape[1], weight.shape[0]):
+            return conv3x3_halo(x, weight, False, bias)
         return conv3x3_tcgen05(x, weight, False, bias)
 
     @staticmethod
@@ -249,7 +275,10 @@ class _Conv3x3Fn(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[1]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            if _lib().drc_conv3x3_supported(x.shape[2], x.shape[3], cin, cout, 1):
+            if _halo_ok(x.shape[2], x.shape[3], cin, cout):
+                backend_counters["tcgen05"] += 1
+                dx = conv3x3_halo(dy, weight, True)
+            elif _lib().drc_conv3x3_supported(x.shape[2], x.shape[3], cin, cout, 1):
                 backend_counters["tcgen05"] += 1
                 dx = conv3x3_tcgen05(dy, weight, True)
             else:
@@ -285,7 +314,7 @@ class Conv2d(nn.Conv2d):
                 and self.groups == 1 and x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
                 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
                 and self.weight.is_contiguous(memory_format=torch.channels_last)
-                and os.environ.get("DRACO_CONV3X3", "cudnn") == "tcgen05"
+                and os.environ.get("DRACO_CONV3X3", "cudnn") in ("tcgen05", "halo")
                 and bool(_lib().drc_conv3x3_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, 0)))
 
     def _strided_ok(self, x: torch.Tensor) -> bool:

@@ -246,3 +246,24 @@ def test_conv_stem_native_kernels(n, hw):
     wref = torch.nn.grad.conv2d_weight(x.float(), (64, 3, 3, 3), dy.float(), padding=1)
     assert dw.shape == wref.shape and _rel_err(dw, wref) < 1e-2, _rel_err(dw, wref)
     assert torch.equal(conv_stem_wgrad(dy, x), dw)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DRACO_EXPERIMENTAL", "0") != "1",
+                    reason="conv_halo_tcgen05.cu has not run on hardware yet; set DRACO_EXPERIMENTAL=1 (and try DRACO_HALO_DESC=0 / 1)")
+@pytest.mark.parametrize("n,hw", [(4, 32), (128, 32), (3, 16), (16, 64)])
+def test_conv3x3_halo_reuse_kernels(n, hw):
+    """Halo patch loaded once per tile, nine taps through row-shifted UMMA descriptors (64 -> 64 channels)."""
+    from draco_b200.ops.conv import conv3x3_halo
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(n + hw)
+    x = torch.randn(n, 64, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 64, 3, 3, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(64, device=dev)
+    y = conv3x3_halo(x, w, False, b)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1)
+    assert _rel_err(y, ref) < 1.5e-2, _rel_err(y, ref)
+    dy = torch.randn(n, 64, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dx = conv3x3_halo(dy, w, True)
+    dref = torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), padding=1)
+    assert _rel_err(dx, dref) < 1.5e-2, _rel_err(dx, dref)
+    assert torch.equal(conv3x3_halo(x, w, False, b), y)

@@ -43,6 +43,18 @@ for (n, c, k, hw) in [(128, 64, 64, 32), (128, 128, 128, 16), (128, 256, 256, 8)
                  "fprop_tflops": fl / t_f / 1e6, "cudnn_fprop_tflops": fl / t_fc / 1e6})
     print(rows[-1], flush=True)
 if os.environ.get("DRACO_EXPERIMENTAL", "0") == "1":
+    # halo-reuse kernels on the 64 -> 64 layer1 shape vs the per-tap kernel and cuDNN
+    from draco_b200.ops.conv import conv3x3_halo  # noqa: E402
+    try:
+        x = torch.randn(128, 64, 32, 32, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(64, 64, 3, 3, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        row = {"shape": "128x64x32x32 -> 64", "halo_fprop_us": timeit(lambda: conv3x3_halo(x, w)),
+               "halo_dgrad_us": timeit(lambda: conv3x3_halo(x, w, True)), "tap_fprop_us": timeit(lambda: conv3x3_tcgen05(x, w)),
+               "cudnn_fprop_us": timeit(lambda: F.conv2d(x, w, padding=1))}
+        rows.append(row)
+        print(row, flush=True)
+    except Exception as e:  # noqa: BLE001  (keep the rest of the bench alive)
+        print("halo bench failed:", e, flush=True)
     # strided / 1x1 layers of ResNet-18 on the tap-table kernels vs cuDNN (the stride-2 dgrads are cuDNN's slowest kernels here)
     from draco_b200.ops.conv import convg_tcgen05, convg_wgrad_tcgen05  # noqa: E402
     for (n, c, k, hw, ks) in [(128, 64, 128, 32, 3), (128, 128, 256, 16, 3), (128, 256, 512, 8, 3), (128, 64, 128, 32, 1),
