@@ -6,7 +6,8 @@
 //
 //   * the nine weight taps (9 x 8 KB) are loaded ONCE per CTA and stay resident (the CTA is persistent over tiles);
 //   * an M tile is an 8 x 16 pixel block; its (8+2) x (16+2) HALO patch (180 pixel rows x 128 B = 23 KB) is loaded ONCE per
-//     tile by one 4-D TMA box (out-of-image pixels zero-filled);
+//     tile by one 4-D TMA box (out-of-image pixels zero-filled); alternatively the box is 16 pixels wide (`pw` = 16, 36 KB)
+//     so that consecutive 8-row groups are 2048 B apart -- a multiple of the 1024-byte swizzle period;
 //   * the A operand of tap (r, s) is that same shared-memory patch addressed through a row-shifted UMMA descriptor: start
 //     address + (r*10 + s) * 128 B, stride between 8-row groups = 10 rows = 1280 B (an 8-pixel image row is one 8-row group,
 //     the next image row starts 10 patch rows later).  The 128B swizzle is an XOR of address bits [4:6] with bits [7:9], the
@@ -16,7 +17,10 @@
 // one resident patch.  dgrad is the same kernel with mirrored taps and the weight tile read MN-major (same shared-memory image).
 //
 // `desc_mode` selects how the descriptor's 3-bit base-offset field is filled for the row-shifted starts (0: zero,
-// 1: (start_address >> 7) & 7) -- the documentation available offline does not settle it, hardware will.
+// 1: (start_address >> 7) & 7), `pw` the patch row pitch (10 or 16 pixels).  If the MMA unit derives the swizzle phase from
+// absolute address bits, (pw = 10, mode 0) is right and cheapest; if it derives it from the row index inside an 8-row group
+// plus the base offset, only (pw = 16, mode 1) can work.  The documentation available offline does not settle it; the
+// hardware will (four combinations, one test run each).
 //
 // STATUS: compiled for sm_100a, SASS checked, NOT yet run on hardware: opt-in via DRACO_CONV3X3=halo, test gated by
 // DRACO_EXPERIMENTAL=1.
@@ -35,10 +39,9 @@ constexpr int BLOCK_K = 64;          // the 64 reduction channels: ONE K-slice p
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 256;
 constexpr int TW = 8, TH = 16;       // tile = 8 x 16 pixels
-constexpr int PW = TW + 2, PH = TH + 2;
-constexpr int PATCH_ROWS = PW * PH;                  // 180
-constexpr int PATCH_BYTES = PATCH_ROWS * 128;        // 23040
-constexpr int PATCH_STRIDE = 23552;                  // next 1024-byte multiple
+constexpr int PH = TH + 2;                           // patch rows (image rows incl. halo)
+constexpr int PW_MAX = 16;                           // patch row pitch in pixels: 10 (dense) or 16 (8-row groups 1024-B periodic)
+constexpr int PATCH_STRIDE = PW_MAX * PH * 128;      // 36864 = 36 x 1024: stage pitch for either layout
 constexpr int W_TAP_BYTES = BLOCK_N * 128;           // 8 KB
 constexpr int W_BYTES = 9 * W_TAP_BYTES;             // 72 KB
 constexpr int STAGES = 4;
@@ -51,6 +54,7 @@ struct HaloArgs {
   const __nv_bfloat16* bias_bf16;
   int dgrad;
   int desc_mode;
+  int pw;                          // patch row pitch in pixels (10 or 16)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -192,7 +196,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int w0 = (tile % wt) * TW, h0 = ((tile / wt) % ht) * TH, n0 = tile / (wt * ht);
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], PATCH_BYTES);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(a.pw * PH * 128));
         tma_load_4d(s_patch + stage * PATCH_STRIDE, &tmap_x, 0, w0 - 1, h0 - 1, n0, &full_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -216,12 +220,12 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
           const int r = tap / 3, s = tap - 3 * r;
           // fprop: input pixel (y + r - 1, x + s - 1) = patch row (y + r) * 10 + (x + s); dgrad: (y + 1 - r, x + 1 - s) -> (2 - r, 2 - s)
           const int pr = DGRAD ? 2 - r : r, ps = DGRAD ? 2 - s : s;
-          const uint32_t a_addr = patch + (uint32_t)(pr * PW + ps) * 128u;
+          const uint32_t a_addr = patch + (uint32_t)(pr * a.pw + ps) * 128u;
           const uint32_t b_addr = smem_u32(s_w + tap * W_TAP_BYTES);
           const uint32_t boff = a.desc_mode == 1 ? ((a_addr >> 7) & 7u) : 0u;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_desc(a_addr + k * UMMA_K * 2, PW * 128, 1, boff);
+            const uint64_t da = make_desc(a_addr + k * UMMA_K * 2, (uint32_t)a.pw * 128u, 1, boff);
             // weights: K-major rows = Cout (fprop) or MN-major rows = Cout = K (dgrad); 64 rows -> 8 groups of 1024 B
             const uint64_t db = DGRAD ? make_desc(b_addr + k * UMMA_K * 128, 1024, (BLOCK_K * 128) >> 4, 0)
                                       : make_desc(b_addr + k * UMMA_K * 2, 1024, 1, 0);
@@ -305,19 +309,20 @@ extern "C" int drc_conv_halo_supported(int H, int W, int Cin, int Cout) {
 
 // act: [N,H,W,64] bf16 (x for fprop, dy for dgrad); wgt: [64,3,3,64] bf16 (arena layout); out: [N,H,W,64] bf16.
 extern "C" int drc_conv_halo(const void* act, const void* wgt, void* out, int N, int H, int W, int dgrad, const float* bias_f32,
-                             const void* bias_bf16, int desc_mode, int num_sms, int device, cudaStream_t stream) {
+                             const void* bias_bf16, int desc_mode, int patch_w, int num_sms, int device, cudaStream_t stream) {
+  if (patch_w != 10 && patch_w != 16) return -3;
   if (!drc_conv_halo_supported(H, W, 64, 64)) return -1;
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) return -2;
   HaloArgs a;
   a.N = N; a.H = H; a.W = W; a.out = (__nv_bfloat16*)out; a.bias_f32 = bias_f32; a.bias_bf16 = (const __nv_bfloat16*)bias_bf16;
-  a.dgrad = dgrad; a.desc_mode = desc_mode;
+  a.dgrad = dgrad; a.desc_mode = desc_mode; a.pw = patch_w;
   CUtensorMap tx, tw;
   {
     cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
-    cuuint32_t box[4] = {64, PW, PH, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)patch_w, PH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(act), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

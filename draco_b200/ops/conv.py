@@ -69,7 +69,7 @@ def _lib():
         lib.drc_convg_wgrad.restype = C.c_int
         lib.drc_conv_halo_supported.argtypes = [C.c_int] * 4
         lib.drc_conv_halo_supported.restype = C.c_int
-        lib.drc_conv_halo.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr, C.c_int, C.c_int, C.c_int, N.ptr]
+        lib.drc_conv_halo.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr, C.c_int, C.c_int, C.c_int, C.c_int, N.ptr]
         lib.drc_conv_halo.restype = C.c_int
         lib.drc_conv_stem_supported.argtypes = [C.c_int] * 4
         lib.drc_conv_stem_supported.restype = C.c_int
@@ -240,7 +240,7 @@ class _ConvGFn(torch.autograd.Function):
 
 def _halo_ok(h: int, w: int, cin: int, cout: int) -> bool:
     """Halo-reuse kernels (csrc/cuda/conv_halo_tcgen05.cu) for the 64 -> 64 layers: opt-in with DRACO_CONV3X3=halo (never run
-    on hardware yet; DRACO_HALO_DESC=0|1 selects the descriptor base-offset convention to try)."""
+    on hardware yet; DRACO_HALO_DESC=0|1 and DRACO_HALO_PW=10|16 select the descriptor convention / patch pitch to try)."""
     return os.environ.get("DRACO_CONV3X3", "cudnn") == "halo" and bool(_lib().drc_conv_halo_supported(h, w, cin, cout))
 
 
@@ -253,7 +253,8 @@ def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, b
     bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
     bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
     N.check(_lib().drc_conv_halo(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, int(dgrad), bf32, bb16,
-                                 int(os.environ.get("DRACO_HALO_DESC", "0")), K.sm_count(act.device), act.device.index,
+                                 int(os.environ.get("DRACO_HALO_DESC", "0")), int(os.environ.get("DRACO_HALO_PW", "10")),
+                                 K.sm_count(act.device), act.device.index,
                                  torch.cuda.current_stream().cuda_stream), "conv_halo")
     return out
 

@@ -252,8 +252,13 @@ def test_conv_stem_native_kernels(n, hw):
 @pytest.mark.skipif(__import__("os").environ.get("DRACO_EXPERIMENTAL", "0") != "1",
                     reason="conv_halo_tcgen05.cu has not run on hardware yet; set DRACO_EXPERIMENTAL=1 (and try DRACO_HALO_DESC=0 / 1)")
 @pytest.mark.parametrize("n,hw", [(4, 32), (128, 32), (3, 16), (16, 64)])
-def test_conv3x3_halo_reuse_kernels(n, hw):
-    """Halo patch loaded once per tile, nine taps through row-shifted UMMA descriptors (64 -> 64 channels)."""
+@pytest.mark.parametrize("pw,desc", [(10, 0), (10, 1), (16, 0), (16, 1)])
+def test_conv3x3_halo_reuse_kernels(n, hw, pw, desc, monkeypatch):
+    """Halo patch loaded once per tile, nine taps through row-shifted UMMA descriptors (64 -> 64 channels).  The four
+    (patch pitch, base-offset convention) combinations are all run: at least one must be numerically right -- see the header of
+    csrc/cuda/conv_halo_tcgen05.cu; keep the cheapest passing one as the default."""
+    monkeypatch.setenv("DRACO_HALO_PW", str(pw))
+    monkeypatch.setenv("DRACO_HALO_DESC", str(desc))
     from draco_b200.ops.conv import conv3x3_halo
     dev = torch.device("cuda", 0)
     torch.manual_seed(n + hw)
