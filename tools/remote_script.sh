@@ -7,7 +7,7 @@ KEY=${1:?usage: remote_script.sh <ssh-key.pem> [user] [repo-dir]}
 USER_=${2:-ubuntu}
 REPO=${3:-draco_b200}
 mkdir -p ~/.ssh && cp "$KEY" ~/.ssh/id_cluster && chmod 600 ~/.ssh/id_cluster
-cat "$(dirname "$0")/config" >> ~/.ssh/config 2>/dev/null || true
+cat "$(dirname "$0")/ssh_config.cluster" >> ~/.ssh/config 2>/dev/null || true
 [ -f ~/hosts ] && sudo sh -c "grep -v deeplearning-worker /etc/hosts > /tmp/hosts.new; cat /tmp/hosts.new $HOME/hosts > /etc/hosts" || true
 SSH_OPTS="-o StrictHostKeyChecking=no -o UserKnownHostsFile=/dev/null -i $HOME/.ssh/id_cluster"
 tail -n +2 ~/hosts_address | while read -r ip; do
