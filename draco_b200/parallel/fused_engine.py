@@ -83,6 +83,10 @@ class FusedEngine:
                                if ns > 1 and cfg.err_mode != "omniscient" and not cfg.profile_phases and not cfg.debug_checksum
                                else [])
         self.push_counters = torch.zeros(cfg.num_workers + 1, dtype=torch.int32, device=device)
+        # does ANY process of the job host several workers on concurrent streams?  (decides the BatchNorm variant job-wide)
+        self.job_uses_worker_streams = (int(cfg.worker_streams) > 1 and cfg.err_mode != "omniscient" and not cfg.profile_phases
+                                        and not cfg.debug_checksum
+                                        and max(len(self.place.local_workers(p)) for p in range(nprocs)) > 1)
         self._staged_step = -1
 
         if cfg.deterministic:
@@ -239,8 +243,16 @@ class FusedEngine:
                 for st, _ in self.worker_streams[: len(order)]:
                     main.wait_stream(st)
             else:
-                for w in order:
-                    n += self._enqueue_worker(w, step_host, self.push_stream)
+                from ..ops import norm as _norm
+                # Replicas of a vote group may live on different GPUs: every rank must run the SAME BatchNorm variant or their
+                # gradients stop being bit-identical.  If any rank of the job runs its workers on concurrent streams (which
+                # forces the two-kernel form), this rank uses the two-kernel form too.
+                _norm.FORCE_COOP = 0 if self.job_uses_worker_streams else None
+                try:
+                    for w in order:
+                        n += self._enqueue_worker(w, step_host, self.push_stream)
+                finally:
+                    _norm.FORCE_COOP = None
         if self.local_workers:
             comp_phase.__exit__(None, None, None)
             nvtx.range_pop()
