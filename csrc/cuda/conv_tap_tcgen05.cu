@@ -14,21 +14,20 @@
 // 9-tap instance of the same kernel.  Motivation (profiles/worker_profile_ResNet18_fused.txt): the three stride-2 dgrads
 // of ResNet-18 cost 220 us of a 2.0 ms step in cuDNN (93 us each for the two large ones) -- 5-10x their FLOP time.
 //
-// STATUS: numerics validated on a B200 (tests/test_gemm_gpu.py::test_convg_*: fprop / dgrad / wgrad for stride 1 and 2, 1x1 and
-// 3x3, plus the autograd path) at the very end of round 1; not yet timed against cuDNN, hence still opt-in via
-// DRACO_CONV_STRIDED=tcgen05 (round-2 first item: `bash tools/gpu_ci.sh experimental worker_native`).
+// The epilogue (conv_epilogue.cuh) stages the bf16 tile in swizzled shared memory, stores it with ONE TMA tensor store per
+// 64-channel half and can reduce it per channel for the BatchNorm that follows (statistics pass fused into the convolution);
+// the stride-2 dgrad parity classes, whose output pixels are strided, keep the direct-store epilogue.
 //
 // Reference counterpart: the strided nn.Conv2d layers of src/model_ops/resnet.py:14-64 (downsampling blocks + shortcuts).
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "conv_epilogue.cuh"
+#include "tcgen05_common.cuh"
 
 namespace {
 
+using namespace tc;
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 256;
 constexpr int MAX_TAPS = 9;
 
@@ -45,109 +44,29 @@ struct TapConvArgs {
   __nv_bfloat16* out;          // [N, out_H, out_W, Cn]
   const float* bias_f32;
   const __nv_bfloat16* bias_bf16;
+  convepi::BnStatArgs stat;    // BatchNorm statistics of the output (TMA-store epilogue only)
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  const uint32_t addr = smem_u32(bar);
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b32 r;\n\t"
-      "elect.sync r|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  const uint64_t sbo = 1024 >> 4;
-  const uint64_t lbo = MN_MAJOR ? ((BLOCK_K * 128) >> 4) : 1;
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= lbo << 16;
-  d |= sbo << 32;
-  d |= 1ull << 46;
-  d |= 2ull << 61;
-  return d;
+  return MN_MAJOR ? desc_mnmajor(smem_addr, BLOCK_K * 128) : desc_kmajor(smem_addr);
 }
 
-template <int BLOCK_N, bool B_MN>
-__device__ __forceinline__ uint32_t make_idesc() {
-  uint32_t d = 0;
-  d |= 1u << 4;
-  d |= 1u << 7;
-  d |= 1u << 10;
-  d |= (B_MN ? 1u : 0u) << 16;
-  d |= (uint32_t)(BLOCK_N >> 3) << 17;
-  d |= (uint32_t)(BLOCK_M >> 4) << 24;
-  return d;
-}
-
-template <int BLOCK_N, int STAGES, bool B_MN>
+template <int BLOCK_N, int STAGES, bool B_MN, bool TMA_EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TapConvArgs a) {
+convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ CUtensorMap tmap_out, const TapConvArgs a) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  constexpr int TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
+  constexpr int EPI_BYTES = TMA_EPI ? convepi::staging_bytes(BLOCK_N) + convepi::stat_bytes() : 0;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* sbuf = smem + STAGES * STAGE_BYTES;                                   // staging tile (1024-aligned: STAGE_BYTES % 1024 == 0)
+  float* s_stat = reinterpret_cast<float*>(sbuf + (TMA_EPI ? convepi::staging_bytes(BLOCK_N) : 0));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -161,19 +80,21 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const int num_tiles = m_tiles * n_tiles;
   const int c_blocks = a.Cred / BLOCK_K;           // 64-channel slices per tap
   const int k_blocks = a.ntaps * c_blocks;
+  const bool want_stats = TMA_EPI && a.stat.partial != nullptr;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    if (TMA_EPI) prefetch_tmap(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_base_slot);
+  if (TMA_EPI && warp >= 4) {
+    for (int i = threadIdx.x - 128; i < 4 * convepi::STAT_MAX_C; i += convepi::EPI_THREADS) s_stat[i] = 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -209,7 +130,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      const uint32_t idesc = make_idesc<BLOCK_N, B_MN>();
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, false, B_MN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -238,58 +159,74 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
+    const int et = threadIdx.x - 128;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / n_tiles, n0 = (tile % n_tiles) * BLOCK_N;
       const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int m = q * 32 + lane;                             // row of the tile = pixel of the patch (w fastest)
-      const int pw = w0 + m % a.BW, ph = h0 + (m / a.BW) % a.BH, pn = nb0 + m / (a.BW * a.BH);
-      const bool row_ok = pn < a.N;
-      __nv_bfloat16* orow = a.out + (((long long)pn * a.out_H + (ph * a.out_mul + a.out_oh)) * a.out_W + (pw * a.out_mul + a.out_ow)) * a.Cn;
+      if (TMA_EPI) {
+        int valid_rows = (a.N - nb0) * a.BW * a.BH;
+        if (valid_rows > BLOCK_M) valid_rows = BLOCK_M;
+        convepi::drain_tile<BLOCK_N>(tmem_base + (uint32_t)(acc * BLOCK_N), sbuf, s_stat, et, valid_rows, n0, a.Cn, a.bias_f32,
+                                     a.bias_bf16, &tmem_empty[acc]);
+        if (et == 0) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            if (n0 + 64 * j < a.Cn) tma_store_4d(&tmap_out, sbuf + j * (128 * 128), n0 + 64 * j, w0, h0, nb0);
+          tma_store_commit();
+        }
+        if (want_stats) convepi::accumulate_stats<BLOCK_N>(sbuf, s_stat, et, valid_rows, n0, a.Cn);
+      } else {
+        const int m = q * 32 + lane;                             // row of the tile = pixel of the patch (w fastest)
+        const int pw = w0 + m % a.BW, ph = h0 + (m / a.BW) % a.BH, pn = nb0 + m / (a.BW * a.BH);
+        const bool row_ok = pn < a.N;
+        __nv_bfloat16* orow = a.out + (((long long)pn * a.out_H + (ph * a.out_mul + a.out_oh)) * a.out_W + (pw * a.out_mul + a.out_ow)) * a.Cn;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
-        const int col0 = n0 + c;
-        if (row_ok && col0 < a.Cn) {
-          float f[32];
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
+          const int col0 = n0 + c;
+          if (row_ok && col0 < a.Cn) {
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (a.bias_f32 || a.bias_bf16) {
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (a.bias_f32 || a.bias_bf16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < a.Cn) f[j] += a.bias_f32 ? a.bias_f32[col0 + j] : __bfloat162float(a.bias_bf16[col0 + j]);
-          }
-          __nv_bfloat16* dst = orow + col0;
-          if (col0 + 32 <= a.Cn) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              uint4 o;
-              o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-              o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(dst + j) = o;
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < a.Cn) f[j] += a.bias_f32 ? a.bias_f32[col0 + j] : __bfloat162float(a.bias_bf16[col0 + j]);
             }
-          } else {
+            __nv_bfloat16* dst = orow + col0;
+            if (col0 + 32 <= a.Cn) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < a.Cn) dst[j] = __float2bfloat16_rn(f[j]);
+              for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(f + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < a.Cn) dst[j] = __float2bfloat16_rn(f[j]);
+            }
           }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TMA_EPI && et == 0) tma_store_wait<0>();                 // every tile of this CTA is in global memory
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (want_stats) {
+    // one tile per CTA (tiles <= grid): slot = M tile, this CTA owns its N-tile's channels; otherwise slot = CTA, all channels
+    const bool one_tile = num_tiles <= (int)gridDim.x;
+    const int mt = blockIdx.x / n_tiles, n0 = (blockIdx.x % n_tiles) * BLOCK_N;
+    const int c_hi = n0 + BLOCK_N < a.Cn ? n0 + BLOCK_N : a.Cn;
+    convepi::finalize_stats<NUM_THREADS>(a.stat, s_stat, convepi::EPI_THREADS / BLOCK_N, a.Cn, one_tile ? mt : (int)blockIdx.x,
+                                         one_tile ? m_tiles : (int)gridDim.x, one_tile ? n0 : 0, one_tile ? c_hi : a.Cn,
+                                         reinterpret_cast<float*>(sbuf));
   }
 }
 
@@ -309,7 +246,7 @@ convg_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;            // 2 atoms of [64 px][64 co]
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  constexpr int TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -330,18 +267,15 @@ convg_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
   const int k_per_split = (k_total + a.splits - 1) / a.splits;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_dy) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(&tmap_x);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_base_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -380,8 +314,7 @@ convg_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      uint32_t idesc = make_idesc<BLOCK_N, true>();
-      idesc |= 1u << 15;                                      // A is MN-major too
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, true, true);      // both operands MN-major
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
@@ -446,9 +379,7 @@ convg_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 __global__ void wgradg_reduce_kernel(const float* partial, int splits, long long elems, __nv_bfloat16* out) {
@@ -465,28 +396,14 @@ __global__ void wgradg_reduce_kernel(const float* partial, int splits, long long
   *reinterpret_cast<uint2*>(out + i) = o;
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
-}
-
-
-template <int BLOCK_N, bool B_MN>
-int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const TapConvArgs& a, int num_sms, cudaStream_t stream) {
+template <int BLOCK_N, bool B_MN, bool TMA_EPI>
+int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const TapConvArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2;
-  constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  auto kern = convg_tcgen05_kernel<BLOCK_N, STAGES, B_MN>;
+  constexpr int EPI_BYTES = TMA_EPI ? convepi::staging_bytes(BLOCK_N) + convepi::stat_bytes() : 0;
+  constexpr int BUDGET = 200 * 1024 - EPI_BYTES;
+  constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  auto kern = convg_tcgen05_kernel<BLOCK_N, STAGES, B_MN, TMA_EPI>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -496,8 +413,15 @@ int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const TapConvArgs& a,
   const int m_tiles = (a.OW / a.BW) * (a.OH / a.BH) * ((a.N + a.BN - 1) / a.BN);
   const int tiles = m_tiles * ((a.Cn + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, SMEM, stream>>>(tx, tw, a);
+  kern<<<grid, NUM_THREADS, SMEM, stream>>>(tx, tw, tout, a);
   return (int)cudaGetLastError();
+}
+
+template <bool B_MN, bool TMA_EPI>
+int launch_n(int block_n, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const TapConvArgs& a, int num_sms,
+             cudaStream_t stream) {
+  return block_n == 64 ? launch_g<64, B_MN, TMA_EPI>(tx, tw, tout, a, num_sms, stream)
+                       : launch_g<128, B_MN, TMA_EPI>(tx, tw, tout, a, num_sms, stream);
 }
 
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -507,17 +431,6 @@ void patch_shape(int OH, int OW, int pixels, int& BW, int& BH, int& BN) {
   BW = OW < pixels ? OW : pixels;
   BH = (pixels / BW) < OH ? (pixels / BW) : OH;
   BN = pixels / (BW * BH);
-}
-
-int encode_act(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int C, int W, int H, int N, int bw, int bh, int bn, int estride) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  // with a traversal stride e the box is given as its bounding size: e * (elements wanted)
-  cuuint32_t box[4] = {64, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), (cuuint32_t)bn};
-  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
-  return (int)enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 }  // namespace
@@ -558,46 +471,75 @@ extern "C" int drc_convg_supported(int H, int W, int Cin, int Cout, int ks, int 
 // fprop (dgrad == 0): act = x [N,H,W,Cin]      -> out = y  [N,H/stride,W/stride,Cout]
 // dgrad (dgrad == 1): act = dy[N,H/s,W/s,Cout] -> out = dx [N,H,W,Cin]
 // wgt: [Cout, ks, ks, Cin] bf16 (arena layout).  H, W are always the spatial size of the forward INPUT x.
+// tma_store: 1 = staged TMA-store epilogue where the output is dense (everything but the stride-2 dgrad parity classes).
+// stat_*: optional BatchNorm statistics of y (fprop + TMA-store epilogue only): workspace of drc_convg_stat_slots() * 2 * Cout
+// floats, a zeroed ticket counter, outputs mean / invstd [Cout], optional running statistics (momentum update).
+extern "C" int drc_convg_stat_slots(int N, int H, int W, int Cout, int stride, int num_sms) {
+  const int OH = H / stride, OW = W / stride;
+  int BW, BH, BN;
+  patch_shape(OH, OW, BLOCK_M, BW, BH, BN);
+  const int m_tiles = (OW / BW) * (OH / BH) * ((N + BN - 1) / BN);
+  const int block_n = Cout >= 128 ? 128 : 64;
+  const int tiles = m_tiles * ((Cout + block_n - 1) / block_n);
+  return tiles <= num_sms ? m_tiles : num_sms;
+}
+
 extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int H, int W, int Cin, int Cout, int ks, int stride,
-                         int dgrad, const float* bias_f32, const void* bias_bf16, int num_sms, int device, cudaStream_t stream) {
+                         int dgrad, const float* bias_f32, const void* bias_bf16, int tma_store, float* stat_partial,
+                         unsigned int* stat_counter, float* stat_mean, float* stat_invstd, float* running_mean, float* running_var,
+                         float eps, float momentum, int num_sms, int device, cudaStream_t stream) {
   if (!drc_convg_supported(H, W, Cin, Cout, ks, stride)) return -1;
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return -2;
   const int OH = H / stride, OW = W / stride;
   TapConvArgs a;
   a.N = N; a.OH = OH; a.OW = OW;                 // both passes iterate over an OH x OW grid per image (dgrad: per parity class)
   a.Cred = dgrad ? Cout : Cin; a.Cn = dgrad ? Cin : Cout;
   patch_shape(OH, OW, BLOCK_M, a.BW, a.BH, a.BN);
   a.out = (__nv_bfloat16*)out; a.bias_f32 = bias_f32; a.bias_bf16 = (const __nv_bfloat16*)bias_bf16;
+  a.stat.partial = nullptr; a.stat.counter = stat_counter; a.stat.mean = stat_mean; a.stat.invstd = stat_invstd;
+  a.stat.running_mean = running_mean; a.stat.running_var = running_var; a.stat.count = (long long)N * OH * OW;
+  a.stat.eps = eps; a.stat.momentum = momentum;
   const int block_n = a.Cn >= 128 ? 128 : 64;
-  CUtensorMap tx, tw;
-  {
-    // weights as a matrix [Cout rows][ks*ks*Cin cols]
-    cuuint64_t dims[2] = {(cuuint64_t)ks * ks * Cin, (cuuint64_t)Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)ks * ks * Cin * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(dgrad ? BLOCK_K : block_n)};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return 2000 + (int)r;
+  const bool dense_out = !(dgrad && stride > 1);
+  const bool tma_epi = tma_store && dense_out;
+  if (stat_partial) {
+    if (dgrad || !tma_epi || Cout > convepi::STAT_MAX_C || (Cout & 3)) return -4;
+    a.stat.partial = stat_partial;
   }
+  CUtensorMap tx, tw, tout;
+  // weights as a matrix [Cout rows][ks*ks*Cin cols]
+  int r = encode_mat(&tw, wgt, Cout, (long long)ks * ks * Cin, (long long)ks * ks * Cin, dgrad ? BLOCK_K : block_n);
+  if (r) return 2000 + r;
+  tout = tw;                                      // placeholder when the direct epilogue is used (never dereferenced)
   if (!dgrad) {
-    int r = encode_act(enc, &tx, act, Cin, W, H, N, a.BW, a.BH, a.BN, stride);
+    r = encode_act(&tx, act, Cin, W, H, N, a.BW, a.BH, a.BN, stride);
     if (r) return 1000 + r;
     int tidx[MAX_TAPS];
     a.in_mul = stride;
     a.ntaps = drc_convg_taps(ks, stride, 0, 0, 0, a.tap_dh, a.tap_dw, tidx);
     for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
     a.out_H = OH; a.out_W = OW; a.out_mul = 1; a.out_oh = a.out_ow = 0;
-    return block_n == 64 ? launch_g<64, false>(tx, tw, a, num_sms, stream) : launch_g<128, false>(tx, tw, a, num_sms, stream);
+    if (tma_epi) {
+      r = encode_act(&tout, out, Cout, OW, OH, N, a.BW, a.BH, a.BN, 1);
+      if (r) return 3000 + r;
+      return launch_n<false, true>(block_n, tx, tw, tout, a, num_sms, stream);
+    }
+    return launch_n<false, false>(block_n, tx, tw, tout, a, num_sms, stream);
   }
   // dgrad: dy has OH x OW pixels per image and is read with unit stride
-  int r = encode_act(enc, &tx, act, Cout, OW, OH, N, a.BW, a.BH, a.BN, 1);
+  r = encode_act(&tx, act, Cout, OW, OH, N, a.BW, a.BH, a.BN, 1);
   if (r) return 1000 + r;
   a.in_mul = 1; a.out_H = H; a.out_W = W; a.out_mul = stride;
   a.bias_f32 = nullptr; a.bias_bf16 = nullptr;
+  if (tma_epi) {                                  // stride 1: one dense launch
+    int tidx[MAX_TAPS];
+    a.ntaps = drc_convg_taps(ks, 1, 1, 0, 0, a.tap_dh, a.tap_dw, tidx);
+    for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
+    a.out_oh = a.out_ow = 0;
+    r = encode_act(&tout, out, Cin, W, H, N, a.BW, a.BH, a.BN, 1);
+    if (r) return 3000 + r;
+    return launch_n<true, true>(block_n, tx, tw, tout, a, num_sms, stream);
+  }
   bool zeroed = false;
   if (ks == 1 && stride > 1) {                    // empty parity classes exist: zero dx before any class writes into it
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * H * W * Cin * 2, stream);
@@ -619,7 +561,7 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
         continue;
       }
       a.out_oh = ph; a.out_ow = pw;
-      int rc = block_n == 64 ? launch_g<64, true>(tx, tw, a, num_sms, stream) : launch_g<128, true>(tx, tw, a, num_sms, stream);
+      int rc = launch_n<true, false>(block_n, tx, tw, tout, a, num_sms, stream);
       if (rc) return rc;
     }
   }
@@ -661,8 +603,6 @@ extern "C" int drc_convg_wgrad(const void* dy, const void* x, void* dw, float* w
                                int stride, int num_sms, int device, cudaStream_t stream) {
   if (!drc_convg_wgrad_supported(H, W, Cin, Cout, ks, stride)) return -1;
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return -2;
   const int OH = H / stride, OW = W / stride, ntaps = ks * ks;
   WgradGArgs a;
   a.N = N; a.H = OH; a.W = OW; a.Cin = Cin; a.Cout = Cout; a.ks = ks; a.stride = stride; a.pad = ks / 2;
@@ -671,9 +611,9 @@ extern "C" int drc_convg_wgrad(const void* dy, const void* x, void* dw, float* w
   a.partial = ws;
   const int block_n = Cin >= 128 ? 128 : 64;
   CUtensorMap tdy, tx;
-  int r = encode_act(enc, &tdy, dy, Cout, OW, OH, N, a.PW, a.PH, a.PN, 1);
+  int r = encode_act(&tdy, dy, Cout, OW, OH, N, a.PW, a.PH, a.PN, 1);
   if (r) return 1000 + r;
-  r = encode_act(enc, &tx, x, Cin, W, H, N, a.PW, a.PH, a.PN, stride);
+  r = encode_act(&tx, x, Cin, W, H, N, a.PW, a.PH, a.PN, stride);
   if (r) return 2000 + r;
   const int out_tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * ntaps * ((Cin + block_n - 1) / block_n);
   const int work = out_tiles * a.splits;

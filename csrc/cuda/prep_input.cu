@@ -5,7 +5,6 @@
 // C <= 4), reading the C planes of the uint8 source and writing C consecutive elements of the NHWC destination.
 // Reference counterpart: the ToTensor + Normalize transforms of src/util.py:28-52.
 //
-// STATUS: compiled for sm_100a, not yet run on hardware: opt-in via DRACO_FUSED_PREP=1.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

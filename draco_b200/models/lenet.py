@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ..ops.conv import Conv2d
 from ..ops.linear import Linear
 from .split import make_split
 
@@ -21,8 +22,8 @@ class LeNet(nn.Module):
 
     def __init__(self) -> None:
         super().__init__()
-        self.conv1 = nn.Conv2d(1, 20, 5, 1)
-        self.conv2 = nn.Conv2d(20, 50, 5, 1)
+        self.conv1 = Conv2d(1, 20, 5, 1)          # ops.conv.Conv2d: native kernels where the geometry is served
+        self.conv2 = Conv2d(20, 50, 5, 1)
         self.fc1 = Linear(4 * 4 * 50, 500)
         self.fc2 = Linear(500, 10)
 

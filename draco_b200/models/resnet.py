@@ -6,8 +6,9 @@ all convolutions are bias-free.  Parameter-tensor counts / sizes (checked in tes
 ResNet18 62 / 11,173,962; ResNet34 110 / 21,282,122; ResNet50 161 / 23,520,842; ResNet101 314 / 42,512,970;
 ResNet152 467 / 58,156,618.
 
-``num_classes`` / ``stem_stride`` are extensions used by the synthetic-ImageNet benchmark config; the
-defaults reproduce the reference exactly.
+``num_classes`` is an extension (the reference hard-codes 10); ``imagenet_stem=True`` swaps the 3x3 CIFAR stem for the
+7x7 / stride-2 convolution + 3x3 / stride-2 max-pool of the ImageNet ResNets and pools adaptively (BASELINE.json config 5:
+ResNet-50 on synthetic 224x224 ImageNet-shaped data).  The defaults reproduce the reference exactly.
 """
 from __future__ import annotations
 
@@ -28,6 +29,14 @@ def _conv(cin: int, cout: int, k: int, stride: int = 1) -> nn.Conv2d:
     return Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
 
 
+def _shortcut(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Identity or projection (conv1x1 + BN) shortcut; the projection's BatchNorm statistics come from its convolution too."""
+    if len(seq) == 0:
+        return x
+    conv, bn = seq[0], seq[1]
+    return bn(conv(x, bn=bn))
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
@@ -43,9 +52,9 @@ class BasicBlock(nn.Module):
                                           FusedBatchNorm2d(planes * self.expansion))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = self.bn1(self.conv1(x), relu=True)
+        out = self.bn1(self.conv1(x, bn=self.bn1), relu=True)      # conv epilogue delivers bn1's batch statistics
         # bn2 + shortcut add + relu in one pass (ops/norm.py)
-        return self.bn2(self.conv2(out), residual=self.shortcut(x), relu=True)
+        return self.bn2(self.conv2(out, bn=self.bn2), residual=_shortcut(self.shortcut, x), relu=True)
 
 
 class Bottleneck(nn.Module):
@@ -65,19 +74,24 @@ class Bottleneck(nn.Module):
                                           FusedBatchNorm2d(planes * self.expansion))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = self.bn1(self.conv1(x), relu=True)
-        out = self.bn2(self.conv2(out), relu=True)
-        return self.bn3(self.conv3(out), residual=self.shortcut(x), relu=True)
+        out = self.bn1(self.conv1(x, bn=self.bn1), relu=True)
+        out = self.bn2(self.conv2(out, bn=self.bn2), relu=True)
+        return self.bn3(self.conv3(out, bn=self.bn3), residual=_shortcut(self.shortcut, x), relu=True)
 
 
 class ResNet(nn.Module):
     input_shape = (3, 32, 32)
 
-    def __init__(self, block: Type[nn.Module], num_blocks: List[int], num_classes: int = 10) -> None:
+    def __init__(self, block: Type[nn.Module], num_blocks: List[int], num_classes: int = 10, imagenet_stem: bool = False) -> None:
         super().__init__()
         self.num_classes = num_classes
         self.in_planes = 64
-        self.conv1 = _conv(3, 64, 3)
+        self.imagenet_stem = imagenet_stem
+        if imagenet_stem:
+            self.input_shape = (3, 224, 224)
+            self.conv1 = Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        else:
+            self.conv1 = _conv(3, 64, 3)
         self.bn1 = FusedBatchNorm2d(64)
         self.layer1 = self._make_layer(block, 64, num_blocks[0], 1)
         self.layer2 = self._make_layer(block, 128, num_blocks[1], 2)
@@ -93,7 +107,9 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = self.bn1(self.conv1(x), relu=True)
+        out = self.bn1(self.conv1(x, bn=self.bn1), relu=True)
+        if self.imagenet_stem:
+            out = F.max_pool2d(out, kernel_size=3, stride=2, padding=1)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
         out = F.adaptive_avg_pool2d(out, 1) if out.shape[-1] != 4 else F.avg_pool2d(out, 4)
         return self.linear(out.flatten(1))
@@ -117,8 +133,8 @@ def _factory(depth: str, split: bool):
     block, blocks = _CFG[depth]
     cls = ResNetSplit if split else ResNet
 
-    def make(num_classes: int = 10):
-        return cls(block, blocks, num_classes=num_classes)
+    def make(num_classes: int = 10, imagenet_stem: bool = False):
+        return cls(block, blocks, num_classes=num_classes, imagenet_stem=imagenet_stem)
 
     make.__name__ = ("ResNetSplit" if split else "ResNet") + depth
     make.__doc__ = f"ResNet-{depth} (CIFAR variant){' with split-backward drivers' if split else ''}."

@@ -18,6 +18,7 @@ from typing import List, Union
 import torch
 from torch import nn
 
+from ..ops.conv import Conv2d
 from ..ops.linear import Linear
 from ..ops.norm import FusedBatchNorm2d
 from .split import make_split
@@ -30,6 +31,21 @@ CFG = {
 }
 
 
+class _Features(nn.Sequential):
+    """``nn.Sequential`` (same numbering / state_dict keys) that hands each convolution the BatchNorm that follows it, so that
+    the convolution epilogue produces the batch statistics (ops/conv.py: ``Conv2d.forward(x, bn=...)``)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        mods = list(self)
+        for i, m in enumerate(mods):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(m, Conv2d) and isinstance(nxt, FusedBatchNorm2d):
+                x = m(x, bn=nxt)
+            else:
+                x = m(x)
+        return x
+
+
 def make_layers(cfg: List[Union[int, str]], batch_norm: bool = False) -> nn.Sequential:
     layers: List[nn.Module] = []
     cin = 3
@@ -37,7 +53,7 @@ def make_layers(cfg: List[Union[int, str]], batch_norm: bool = False) -> nn.Sequ
         if v == "M":
             layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
             continue
-        layers.append(nn.Conv2d(cin, int(v), kernel_size=3, padding=1))
+        layers.append(Conv2d(cin, int(v), kernel_size=3, padding=1))
         if batch_norm:
             # BN + ReLU fused (ops/norm.py); the Identity keeps torchvision's module numbering / state_dict keys
             layers.append(FusedBatchNorm2d(int(v), relu=True))
@@ -45,7 +61,7 @@ def make_layers(cfg: List[Union[int, str]], batch_norm: bool = False) -> nn.Sequ
         else:
             layers.append(nn.ReLU(inplace=True))
         cin = int(v)
-    return nn.Sequential(*layers)
+    return _Features(*layers)
 
 
 class VGG(nn.Module):

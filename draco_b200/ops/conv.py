@@ -1,12 +1,10 @@
-"""Convolution layer whose pointwise (1x1, stride 1) case runs on the hand-written tcgen05 GEMM.
-
-In NHWC a 1x1 convolution *is* a GEMM: ``y[N*H*W, Cout] = x[N*H*W, Cin] @ W[Cout, Cin]^T`` -- both operands K-major, no
-im2col, no layout change (weights live in the arena as ``[Cout, kH, kW, Cin]``).  The three products of the layer map onto
-``csrc/cuda/gemm_tcgen05.cu`` exactly like a Linear layer (ops/linear.py): fprop K-major x K-major, dgrad with an
-MN-major B, wgrad with MN-major A and B (K = N*H*W).  This covers two thirds of the convolutions of the bottleneck
-ResNets (50/101/152: conv1, conv3 and the stride-1 projection shortcuts).  Everything else -- 3x3, strided -- goes to
-cuDNN's implicit-GEMM kernels in deterministic mode unless ``DRACO_CONV3X3=tcgen05`` selects the TMA-patch implicit-GEMM
-kernels of ``csrc/cuda/conv_tcgen05.cu`` (fprop, dgrad and split-K wgrad) for the 3x3 / stride-1 layers.  ``backend_counters`` records which path served each call.
+"""Convolution layer served by this repository's sm_100a kernels (see ``Conv2d``): tcgen05 tap-table / halo-reuse implicit GEMM
+for 3x3 and 1x1 convolutions with stride 1 or 2 (fprop, dgrad, split-K wgrad; csrc/cuda/conv_tap_tcgen05.cu,
+conv_halo_tcgen05.cu), the tcgen05 GEMM for the remaining pointwise layers (csrc/cuda/gemm_tcgen05.cu) and CUDA-core kernels
+for the 3-channel stem (csrc/cuda/conv_stem.cu).  In NHWC a 1x1 convolution *is* a GEMM:
+``y[N*H*W, Cout] = x[N*H*W, Cin] @ W[Cout, Cin]^T`` -- both operands K-major, no im2col, no layout change (weights live in the
+arena as ``[Cout, kH, kW, Cin]``).  The convolution epilogue can also produce the BatchNorm statistics of its output
+(``BnStatRequest``).  ``backend_counters`` records which path served each call; ``DRACO_CONV=cudnn`` forces the library.
 
 Reference counterpart: ``nn.Conv2d`` inside src/model_ops/resnet.py:14-64 / vgg.py:46-59 (PyTorch-0.3 CPU THNN).
 """
@@ -47,19 +45,12 @@ def _lib():
     from .. import _native as N
     lib = N.cuda()
     if not getattr(lib, "_conv_ready", False):
-        lib.drc_conv3x3_supported.argtypes = [C.c_int] * 5
-        lib.drc_conv3x3_supported.restype = C.c_int
-        lib.drc_conv3x3.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 6 + [N.ptr, N.ptr, C.c_int, C.c_int, N.ptr]
-        lib.drc_conv3x3.restype = C.c_int
-        lib.drc_conv3x3_wgrad_supported.argtypes = [C.c_int] * 4
-        lib.drc_conv3x3_wgrad_supported.restype = C.c_int
-        lib.drc_conv3x3_wgrad_plan.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_longlong)]
-        lib.drc_conv3x3_wgrad_plan.restype = C.c_int
-        lib.drc_conv3x3_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 7 + [N.ptr]
-        lib.drc_conv3x3_wgrad.restype = C.c_int
         lib.drc_convg_supported.argtypes = [C.c_int] * 6
         lib.drc_convg_supported.restype = C.c_int
-        lib.drc_convg.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 8 + [N.ptr, N.ptr, C.c_int, C.c_int, N.ptr]
+        lib.drc_convg_stat_slots.argtypes = [C.c_int] * 6
+        lib.drc_convg_stat_slots.restype = C.c_int
+        lib.drc_convg.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 8 + [N.ptr, N.ptr, C.c_int] + [N.ptr] * 6
+                                  + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
         lib.drc_convg.restype = C.c_int
         lib.drc_convg_wgrad_supported.argtypes = [C.c_int] * 6
         lib.drc_convg_wgrad_supported.restype = C.c_int
@@ -69,13 +60,16 @@ def _lib():
         lib.drc_convg_wgrad.restype = C.c_int
         lib.drc_conv_halo_supported.argtypes = [C.c_int] * 4
         lib.drc_conv_halo_supported.restype = C.c_int
-        lib.drc_conv_halo.argtypes = [N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr, C.c_int, C.c_int, C.c_int, C.c_int, N.ptr]
+        lib.drc_conv_halo_stat_slots.argtypes = [C.c_int] * 4
+        lib.drc_conv_halo_stat_slots.restype = C.c_int
+        lib.drc_conv_halo.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr] + [N.ptr] * 6
+                                      + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
         lib.drc_conv_halo.restype = C.c_int
         lib.drc_conv_stem_supported.argtypes = [C.c_int] * 4
         lib.drc_conv_stem_supported.restype = C.c_int
         lib.drc_conv_stem_wgrad_parts.argtypes = [C.c_int] * 4
         lib.drc_conv_stem_wgrad_parts.restype = C.c_int
-        lib.drc_conv_stem_fprop.argtypes = [N.ptr] * 4 + [C.c_int] * 4 + [N.ptr]
+        lib.drc_conv_stem_fprop.argtypes = [N.ptr] * 4 + [C.c_int] * 3 + [N.ptr] * 6 + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr]
         lib.drc_conv_stem_fprop.restype = C.c_int
         lib.drc_conv_stem_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 5 + [N.ptr]
         lib.drc_conv_stem_wgrad.restype = C.c_int
@@ -83,52 +77,36 @@ def _lib():
     return lib
 
 
-def conv3x3_wgrad_tcgen05(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """Weight gradient of the 3x3 / stride 1 / pad 1 convolution on the split-K tcgen05 kernel: both operands are read
-    MN-major straight from the NHWC activations (K = pixels), fp32 partials are folded in a fixed order.  Returns
-    [Cout, Cin, 3, 3] in channels-last storage (the arena layout)."""
-    import ctypes as C
-    from .. import _native as N
-    from . import kernels as K
-    lib = _lib()
-    n, cout, h, w = dy.shape
-    cin = x.shape[1]
-    assert dy.is_contiguous(memory_format=torch.channels_last) and x.is_contiguous(memory_format=torch.channels_last)
-    sms = K.sm_count(dy.device)
-    ws_elems = C.c_longlong(0)
-    lib.drc_conv3x3_wgrad_plan(n, h, w, cin, cout, sms, C.byref(ws_elems))
-    ws = torch.empty(ws_elems.value, dtype=torch.float32, device=dy.device)
-    dw = torch.empty((cout, cin, 3, 3), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
-    N.check(lib.drc_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, w, cin, cout, sms,
-                                  dy.device.index, torch.cuda.current_stream().cuda_stream), "conv3x3_wgrad")
-    return dw
+class BnStatRequest:
+    """Asks a convolution to produce the training-mode BatchNorm statistics of its output in its epilogue
+    (csrc/cuda/conv_epilogue.cuh).  ``running_mean`` / ``running_var`` (may be None) receive the momentum update there as well;
+    ``mean`` / ``invstd`` are filled by the call and handed to ``ops.norm`` (which then only runs its apply kernel)."""
+
+    def __init__(self, eps: float, momentum: float, running_mean=None, running_var=None):
+        self.eps, self.momentum = float(eps), float(momentum)
+        self.running_mean, self.running_var = running_mean, running_var
+        self.mean = self.invstd = None
 
 
-def conv3x3_tcgen05(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None) -> torch.Tensor:
-    """3x3 / stride 1 / pad 1 convolution (``dgrad=False``) or its backward-data pass (``dgrad=True``) on the tcgen05
-    implicit-GEMM kernel (csrc/cuda/conv_tcgen05.cu).  ``act``: channels-last bf16 [N, C, H, W]; ``weight``:
-    [Cout, Cin, 3, 3] in channels-last storage ([Cout, 3, 3, Cin] in memory, the arena layout)."""
-    from .. import _native as N
-    from . import kernels as K
-    lib = _lib()
-    n, _, h, w = act.shape
-    cout, cin = weight.shape[0], weight.shape[1]
-    assert act.is_contiguous(memory_format=torch.channels_last) and weight.is_contiguous(memory_format=torch.channels_last)
-    out = torch.empty((n, cin if dgrad else cout, h, w), dtype=torch.bfloat16, device=act.device,
-                      memory_format=torch.channels_last)
-    bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
-    bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
-    N.check(lib.drc_conv3x3(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, cin, cout, int(dgrad), bf32, bb16,
-                            K.sm_count(act.device), act.device.index, torch.cuda.current_stream().cuda_stream), "conv3x3")
-    return out
+def _stat_args(req, cout: int, slots: int, device):
+    """(partial, counter, mean, invstd, running_mean, running_var, eps, momentum) for the C ABI."""
+    if req is None:
+        return (None, None, None, None, None, None, 0.0, 0.0), ()
+    from .norm import _counter
+    partial = torch.empty(slots * 2 * cout, dtype=torch.float32, device=device)
+    req.mean = torch.empty(cout, dtype=torch.float32, device=device)
+    req.invstd = torch.empty(cout, dtype=torch.float32, device=device)
+    rm = req.running_mean.data_ptr() if req.running_mean is not None else None
+    rv = req.running_var.data_ptr() if req.running_var is not None else None
+    return ((partial.data_ptr(), _counter(device)[12:].data_ptr(), req.mean.data_ptr(), req.invstd.data_ptr(), rm, rv, req.eps,
+             req.momentum), (partial,))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# generalised tap-table kernels (csrc/cuda/conv_strided_tcgen05.cu): stride 1 or 2, 1x1 or 3x3.  Numerics validated on
-# hardware, not yet timed against cuDNN: opt-in with DRACO_CONV_STRIDED=tcgen05.
+# tap-table implicit-GEMM kernels (csrc/cuda/conv_tap_tcgen05.cu): stride 1 or 2, 1x1 or 3x3, fprop / dgrad / split-K wgrad
 # ---------------------------------------------------------------------------------------------------------------------
 def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, dgrad: bool = False,
-                  bias: torch.Tensor = None) -> torch.Tensor:
+                  bias: torch.Tensor = None, bn_stats: "BnStatRequest" = None) -> torch.Tensor:
     """``dgrad=False``: ``act`` = x [N, Cin, H, W] -> y [N, Cout, H/stride, W/stride];  ``dgrad=True``: ``act`` = dy -> dx.
     ``in_hw`` is the spatial size of the forward input x; ``weight`` [Cout, Cin, ks, ks] in channels-last storage."""
     from .. import _native as N
@@ -143,8 +121,14 @@ def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, d
     out = torch.empty(oshape, dtype=torch.bfloat16, device=act.device, memory_format=torch.channels_last)
     bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
     bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
+    sms = K.sm_count(act.device)
+    tma = 0 if os.environ.get("DRACO_CONV_EPI", "tma") == "direct" else 1
+    assert bn_stats is None or (tma and not dgrad)
+    slots = lib.drc_convg_stat_slots(n, h, w, cout, stride, sms) if bn_stats is not None else 0
+    st, keep = _stat_args(bn_stats, cout, slots, act.device)
     N.check(lib.drc_convg(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, cin, cout, ks, stride, int(dgrad), bf32, bb16,
-                          K.sm_count(act.device), act.device.index, torch.cuda.current_stream().cuda_stream), "convg")
+                          tma, *st, sms, act.device.index, torch.cuda.current_stream().cuda_stream), "convg")
+    del keep
     return out
 
 
@@ -167,18 +151,47 @@ def convg_wgrad_tcgen05(dy: torch.Tensor, x: torch.Tensor, ks: int, stride: int)
     return dw
 
 
+def halo_supported(h: int, w: int, cin: int, cout: int) -> bool:
+    """Halo-reuse kernel (csrc/cuda/conv_halo_tcgen05.cu): 3x3 / stride 1, 64 -> 64 channels, H % 16 == 0, W % 8 == 0."""
+    return os.environ.get("DRACO_CONV_HALO", "1") != "0" and bool(_lib().drc_conv_halo_supported(h, w, cin, cout))
+
+
+def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None,
+                 bn_stats: "BnStatRequest" = None) -> torch.Tensor:
+    from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
+    n, _, h, w = act.shape
+    assert act.is_contiguous(memory_format=torch.channels_last) and weight.permute(0, 2, 3, 1).is_contiguous()
+    out = torch.empty((n, 64, h, w), dtype=torch.bfloat16, device=act.device, memory_format=torch.channels_last)
+    bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
+    bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
+    sms = K.sm_count(act.device)
+    slots = lib.drc_conv_halo_stat_slots(n, h, w, sms) if bn_stats is not None else 0
+    st, keep = _stat_args(bn_stats, 64, slots, act.device)
+    N.check(lib.drc_conv_halo(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, int(dgrad), bf32, bb16, *st, sms,
+                              act.device.index, torch.cuda.current_stream().cuda_stream), "conv_halo")
+    del keep
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
-# 3-channel stem (csrc/cuda/conv_stem.cu), CUDA cores.  Numerics validated on hardware, not yet timed: opt-in with DRACO_CONV_STEM=native.
+# 3-channel stem (csrc/cuda/conv_stem.cu), CUDA cores.
 # ---------------------------------------------------------------------------------------------------------------------
-def conv_stem_fprop(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:
+def conv_stem_fprop(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, bn_stats: "BnStatRequest" = None) -> torch.Tensor:
     """x: channels-last bf16 [N, 3, H, W]; weight [64, 3, 3, 3] stored [Cout, 3, 3, Cin] -> y channels-last [N, 64, H, W]."""
     from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
     n, _, h, w = x.shape
     assert x.is_contiguous(memory_format=torch.channels_last) and weight.permute(0, 2, 3, 1).is_contiguous()
     y = torch.empty((n, 64, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
     b = bias.float().contiguous() if bias is not None else None
-    N.check(_lib().drc_conv_stem_fprop(x.data_ptr(), weight.data_ptr(), y.data_ptr(), b.data_ptr() if b is not None else None, n, h, w,
-                                       x.device.index, torch.cuda.current_stream().cuda_stream), "conv_stem_fprop")
+    sms = K.sm_count(x.device)
+    st, keep = _stat_args(bn_stats, 64, lib.drc_conv_stem_wgrad_parts(n, h, w, sms) if bn_stats is not None else 0, x.device)
+    N.check(lib.drc_conv_stem_fprop(x.data_ptr(), weight.data_ptr(), y.data_ptr(), b.data_ptr() if b is not None else None, n, h, w,
+                                    *st, sms, x.device.index, torch.cuda.current_stream().cuda_stream), "conv_stem_fprop")
+    del keep
     return y
 
 
@@ -199,155 +212,120 @@ def conv_stem_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 class _ConvStemFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, bn_req):
         ctx.save_for_backward(x)
         ctx.has_bias = bias is not None
-        return conv_stem_fprop(x, weight, bias)
+        y = conv_stem_fprop(x, weight, bias, bn_req)
+        if bn_req is not None:
+            mean, invstd = bn_req.mean, bn_req.invstd
+        else:
+            mean, invstd = x.new_empty(0, dtype=torch.float32), x.new_empty(0, dtype=torch.float32)
+        ctx.mark_non_differentiable(mean, invstd)
+        return y, mean, invstd
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dmean, _dinvstd):
         (x,) = ctx.saved_tensors
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         assert not ctx.needs_input_grad[0], "the stem kernel has no dgrad (network inputs carry no gradient)"
         dw = conv_stem_wgrad(dy, x) if ctx.needs_input_grad[1] else None
         db = dy.sum((0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return None, dw, db
+        return None, dw, db, None
 
 
 class _ConvGFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias, stride):
-        ctx.save_for_backward(x, weight)
-        ctx.stride, ctx.has_bias = stride, bias is not None
-        return convg_tcgen05(x, weight, x.shape[2:], stride, False, bias)
+    """3x3 / 1x1, stride 1 / 2 convolution on the tcgen05 kernels.  Returns (y, mean, invstd); the last two are the fused
+    BatchNorm statistics when ``bn_req`` is given (empty tensors otherwise) and carry no gradient."""
 
     @staticmethod
-    def backward(ctx, dy):
+    def forward(ctx, x, weight, bias, stride, bn_req):
+        ctx.save_for_backward(x, weight)
+        ctx.stride, ctx.has_bias = stride, bias is not None
+        h, w = x.shape[2], x.shape[3]
+        cout, cin, ks = weight.shape[0], weight.shape[1], weight.shape[2]
+        ctx.halo = ks == 3 and stride == 1 and halo_supported(h, w, cin, cout)
+        if ctx.halo:
+            y = conv3x3_halo(x, weight, False, bias, bn_req)
+        else:
+            y = convg_tcgen05(x, weight, (h, w), stride, False, bias, bn_req)
+        if bn_req is not None:
+            mean, invstd = bn_req.mean, bn_req.invstd
+        else:
+            mean, invstd = x.new_empty(0, dtype=torch.float32), x.new_empty(0, dtype=torch.float32)
+        ctx.mark_non_differentiable(mean, invstd)
+        return y, mean, invstd
+
+    @staticmethod
+    def backward(ctx, dy, _dmean, _dinvstd):
         x, weight = ctx.saved_tensors
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = dw = db = None
         backend_counters["tcgen05"] += 1
         if ctx.needs_input_grad[0]:
-            dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True)
+            if ctx.halo:
+                dx = conv3x3_halo(dy, weight, True)
+            else:
+                dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True)
         if ctx.needs_input_grad[1]:
             dw = convg_wgrad_tcgen05(dy, x, weight.shape[2], ctx.stride)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum((0, 2, 3))
-        return dx, dw, db, None
-
-
-def _halo_ok(h: int, w: int, cin: int, cout: int) -> bool:
-    """Halo-reuse kernels (csrc/cuda/conv_halo_tcgen05.cu) for the 64 -> 64 layers: opt-in with DRACO_CONV3X3=halo (never run
-    on hardware yet; DRACO_HALO_DESC=0|1 and DRACO_HALO_PW=10|16 select the descriptor convention / patch pitch to try)."""
-    return os.environ.get("DRACO_CONV3X3", "cudnn") == "halo" and bool(_lib().drc_conv_halo_supported(h, w, cin, cout))
-
-
-def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None) -> torch.Tensor:
-    from .. import _native as N
-    from . import kernels as K
-    n, _, h, w = act.shape
-    assert act.is_contiguous(memory_format=torch.channels_last) and weight.is_contiguous(memory_format=torch.channels_last)
-    out = torch.empty((n, 64, h, w), dtype=torch.bfloat16, device=act.device, memory_format=torch.channels_last)
-    bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
-    bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
-    N.check(_lib().drc_conv_halo(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, int(dgrad), bf32, bb16,
-                                 int(os.environ.get("DRACO_HALO_DESC", "0")), int(os.environ.get("DRACO_HALO_PW", "10")),
-                                 K.sm_count(act.device), act.device.index,
-                                 torch.cuda.current_stream().cuda_stream), "conv_halo")
-    return out
-
-
-class _Conv3x3Fn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        if _halo_ok(x.shape[2], x.shape[3], weight.shape[1], weight.shape[0]):
-            return conv3x3_halo(x, weight, False, bias)
-        return conv3x3_tcgen05(x, weight, False, bias)
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
-        if not dy.is_contiguous(memory_format=torch.channels_last):
-            dy = dy.contiguous(memory_format=torch.channels_last)
-        cout, cin = weight.shape[0], weight.shape[1]
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            if _halo_ok(x.shape[2], x.shape[3], cin, cout):
-                backend_counters["tcgen05"] += 1
-                dx = conv3x3_halo(dy, weight, True)
-            elif _lib().drc_conv3x3_supported(x.shape[2], x.shape[3], cin, cout, 1):
-                backend_counters["tcgen05"] += 1
-                dx = conv3x3_tcgen05(dy, weight, True)
-            else:
-                backend_counters["cudnn"] += 1
-                dx = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-                                                         [True, False, False])[0]
-        if ctx.needs_input_grad[1]:
-            if (os.environ.get("DRACO_CONV3X3_WGRAD", "tcgen05") == "tcgen05"
-                    and _lib().drc_conv3x3_wgrad_supported(x.shape[2], x.shape[3], cin, cout)):
-                backend_counters["tcgen05"] += 1
-                dw = conv3x3_wgrad_tcgen05(dy, x)
-            else:
-                backend_counters["cudnn"] += 1
-                dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-                                                         [False, True, False])[1]
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum((0, 2, 3))
-        return dx, dw, db
+        return dx, dw, db, None, None
 
 
 class Conv2d(nn.Conv2d):
-    """``nn.Conv2d`` (same parameters / state_dict) with the pointwise fast path described above."""
+    """``nn.Conv2d`` (same parameters / state_dict) whose CUDA bf16 channels-last forms run on this repository's kernels:
+
+    * 3x3 and 1x1, stride 1 or 2, channel counts that are multiples of 64 -> tap-table / halo-reuse tcgen05 implicit GEMM;
+    * 1x1 / stride 1 with other channel counts (multiples of 8, >= 64) -> the tcgen05 GEMM on NHWC rows;
+    * the 3-channel 3x3 stem -> CUDA-core kernels of conv_stem.cu;
+    * everything else (CPU, fp32, exotic geometry) -> ``nn.Conv2d`` (counted in ``backend_counters["cudnn"]``).
+
+    ``forward(x, bn=module)`` additionally asks the kernel for the BatchNorm statistics of its output (see BnStatRequest) and
+    leaves them on ``bn`` for the ``FusedBatchNorm2d`` call that follows.  ``DRACO_CONV=cudnn`` forces the library path."""
+
+    def _common_ok(self, x: torch.Tensor) -> bool:
+        return (os.environ.get("DRACO_CONV", "native") == "native" and self.dilation == (1, 1) and self.groups == 1 and x.is_cuda
+                and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16 and x.dim() == 4
+                and x.is_contiguous(memory_format=torch.channels_last) and self.padding_mode == "zeros")
 
     def _pointwise_ok(self, x: torch.Tensor) -> bool:
-        return (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0) and self.dilation == (1, 1)
-                and self.groups == 1 and x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
-                and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
-                and self.in_channels % 8 == 0 and self.out_channels % 8 == 0 and self.in_channels >= 64 and self.out_channels >= 64
-                and os.environ.get("DRACO_CONV1X1", "tcgen05") == "tcgen05")
+        return (self._common_ok(x) and self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0)
+                and self.in_channels % 8 == 0 and self.out_channels % 8 == 0 and self.in_channels >= 64 and self.out_channels >= 64)
 
-    def _conv3x3_ok(self, x: torch.Tensor) -> bool:
-        return (self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1) and self.dilation == (1, 1)
-                and self.groups == 1 and x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
-                and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
-                and self.weight.is_contiguous(memory_format=torch.channels_last)
-                and os.environ.get("DRACO_CONV3X3", "cudnn") in ("tcgen05", "halo")
-                and bool(_lib().drc_conv3x3_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, 0)))
-
-    def _strided_ok(self, x: torch.Tensor) -> bool:
-        """Opt-in path (DRACO_CONV_STRIDED=tcgen05): stride-2 3x3 and 1x1 layers on the tap-table kernels."""
-        if os.environ.get("DRACO_CONV_STRIDED", "cudnn") != "tcgen05":
+    def _tap_ok(self, x: torch.Tensor) -> bool:
+        ks, st = self.kernel_size[0], self.stride[0]
+        if not (self._common_ok(x) and self.kernel_size in ((1, 1), (3, 3)) and self.stride in ((1, 1), (2, 2))
+                and self.padding == (ks // 2, ks // 2) and self.weight.permute(0, 2, 3, 1).is_contiguous()):
             return False
-        ks = self.kernel_size[0]
-        return (self.kernel_size in ((1, 1), (3, 3)) and self.stride == (2, 2) and self.padding == (ks // 2, ks // 2)
-                and self.dilation == (1, 1) and self.groups == 1 and x.is_cuda and x.dtype == torch.bfloat16
-                and self.weight.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
-                and self.weight.permute(0, 2, 3, 1).is_contiguous()
-                and bool(_lib().drc_convg_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, ks, 2))
-                and bool(_lib().drc_convg_wgrad_supported(x.shape[2], x.shape[3], self.in_channels, self.out_channels, ks, 2)))
+        lib = _lib()
+        h, w = x.shape[2], x.shape[3]
+        return (bool(lib.drc_convg_supported(h, w, self.in_channels, self.out_channels, ks, st))
+                and bool(lib.drc_convg_wgrad_supported(h, w, self.in_channels, self.out_channels, ks, st)))
 
     def _stem_ok(self, x: torch.Tensor) -> bool:
-        return (os.environ.get("DRACO_CONV_STEM", "cudnn") == "native" and self.kernel_size == (3, 3) and self.stride == (1, 1)
-                and self.padding == (1, 1) and self.dilation == (1, 1) and self.groups == 1 and self.in_channels == 3
-                and self.out_channels == 64 and x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
-                and x.dim() == 4 and not x.requires_grad and x.is_contiguous(memory_format=torch.channels_last)
+        return (self._common_ok(x) and self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1)
+                and self.in_channels == 3 and self.out_channels == 64 and not x.requires_grad
                 and self.weight.permute(0, 2, 3, 1).is_contiguous()
                 and bool(_lib().drc_conv_stem_supported(x.shape[2], x.shape[3], 3, 64)))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, bn: nn.Module = None) -> torch.Tensor:
         if self._stem_ok(x):
             backend_counters["native_stem"] = backend_counters.get("native_stem", 0) + 1
-            return _ConvStemFn.apply(x, self.weight, self.bias)
-        if self._strided_ok(x):
+            req = bn.stat_request(x, self.out_channels) if (bn is not None and hasattr(bn, "stat_request")) else None
+            y, mean, invstd = _ConvStemFn.apply(x, self.weight, self.bias, req)
+            if req is not None:
+                bn.pending_stats = (y, mean, invstd)
+            return y
+        if self._tap_ok(x):
             backend_counters["tcgen05"] += 1
-            return _ConvGFn.apply(x, self.weight, self.bias, 2)
-        if self._conv3x3_ok(x):
-            backend_counters["tcgen05"] += 1
-            return _Conv3x3Fn.apply(x, self.weight, self.bias)
+            req = bn.stat_request(x, self.out_channels) if (bn is not None and hasattr(bn, "stat_request")) else None
+            y, mean, invstd = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req)
+            if req is not None:
+                bn.pending_stats = (y, mean, invstd)
+            return y
         if not self._pointwise_ok(x):
             backend_counters["cudnn"] += 1
             return super().forward(x)

@@ -56,7 +56,7 @@ class _FusedCE(torch.autograd.Function):
 
 
 def fused_enabled(logits: torch.Tensor) -> bool:
-    return (os.environ.get("DRACO_FUSED_LOSS", "0") == "1" and logits.is_cuda and logits.dim() == 2
+    return (os.environ.get("DRACO_FUSED_LOSS", "1") == "1" and logits.is_cuda and logits.dim() == 2
             and logits.dtype in (torch.bfloat16, torch.float32))
 
 

@@ -3,8 +3,8 @@
 ``FusedBatchNorm2d`` *is* an ``nn.BatchNorm2d`` (same parameters, buffers and state_dict keys as the reference's models,
 src/model_ops/resnet.py:19-24) whose ``forward(x, residual=None, relu=False)`` computes
 ``relu?(batch_norm(x) + residual)``.  On CUDA, in training mode, for bf16 channels-last activations with a power-of-two
-channel count it runs as two streaming kernels per direction (statistics / apply, reduce / apply) with deterministic
-reductions; everywhere else it is exactly ``F.batch_norm`` (+ add, + relu) so CPU runs and evaluation are unchanged.
+channel count it runs as streaming kernels with deterministic reductions (forward: apply only when the producing convolution's epilogue
+delivered the statistics, else statistics + apply; backward: reduce + apply); everywhere else it is exactly ``F.batch_norm`` (+ add, + relu) so CPU runs and evaluation are unchanged.
 ``backend_counters`` records which path served each call.
 """
 from __future__ import annotations
@@ -33,27 +33,14 @@ def _lib():
         lib.drc_bn_workspace.restype = N.i64
         lib.drc_bn_fwd.argtypes = [N.ptr] * 11 + [N.i64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, st]
         lib.drc_bn_fwd.restype = C.c_int
-        lib.drc_bn_bwd.argtypes = [N.ptr] * 13 + [N.i64, C.c_int, C.c_int, C.c_int, C.c_int, st]
+        lib.drc_bn_bwd.argtypes = [N.ptr] * 13 + [N.i64, C.c_int, C.c_int, C.c_int, st]
         lib.drc_bn_bwd.restype = C.c_int
-        lib.drc_bn_cluster_plan.argtypes = [N.i64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-        lib.drc_bn_cluster_plan.restype = C.c_int
-        lib.drc_bn_fwd_cluster.argtypes = [N.ptr] * 9 + [N.i64, C.c_int, C.c_float, C.c_float, C.c_int, st]
-        lib.drc_bn_fwd_cluster.restype = C.c_int
-        lib.drc_bn_bwd_cluster.argtypes = [N.ptr] * 10 + [N.i64, C.c_int, C.c_int, st]
-        lib.drc_bn_bwd_cluster.restype = C.c_int
         lib._bn_ready = True
     return lib
 
 
-def _cluster_path(M: int, c: int) -> bool:
-    """Single-launch cluster kernels (csrc/cuda/bn_cluster.cu) for tensors small enough to sit in one cluster's shared memory
-    per channel slice.  Opt-in (DRACO_BN_CLUSTER=1) until validated and timed on hardware."""
-    return os.environ.get("DRACO_BN_CLUSTER", "0") == "1" and bool(_lib().drc_bn_cluster_plan(M, c, None, None))
-
-
-# Set by the engine when logical workers run on concurrent streams: cooperative (grid-barrier) kernels need the whole GPU
-# to themselves, and only one worker per process may update the shared running statistics.
-FORCE_COOP: Optional[int] = None
+# Set by the engine when logical workers run on concurrent streams: only one worker per process may update the shared
+# running statistics.
 UPDATE_RUNNING_STATS = True
 
 
@@ -89,13 +76,6 @@ def _counter(device: torch.device) -> torch.Tensor:
     return _counter_cache[key]
 
 
-def _coop() -> int:
-    """1: single cooperative kernel per direction (statistics, grid barrier, apply); 0: two kernels."""
-    if FORCE_COOP is not None:
-        return FORCE_COOP
-    return 0 if os.environ.get("DRACO_BN_COOP", "1") == "0" else 1
-
-
 def _sms(device: torch.device) -> int:
     return torch.cuda.get_device_properties(device).multi_processor_count
 
@@ -112,27 +92,27 @@ def fused_supported(x: torch.Tensor, training: bool) -> bool:
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu, mean, invstd):
+        """``mean`` / ``invstd`` given: statistics came out of the producing convolution's epilogue, only the apply kernel runs."""
         lib = _lib()
         n, c, h, w = x.shape
         M = n * h * w
         dev = x.device
         y = torch.empty_like(x, memory_format=torch.channels_last)
-        mean = torch.empty(c, dtype=torch.float32, device=dev)
-        invstd = torch.empty(c, dtype=torch.float32, device=dev)
+        have_stats = mean is not None
         if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
             residual = residual.contiguous(memory_format=torch.channels_last)
-        ctx.cluster = _cluster_path(M, c)
-        if ctx.cluster:
-            N.check(lib.drc_bn_fwd_cluster(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                           _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), M, c, float(eps),
-                                           float(momentum), int(relu), torch.cuda.current_stream().cuda_stream), "bn_fwd_cluster")
+        if have_stats:
+            ws_ptr = None
         else:
+            mean = torch.empty(c, dtype=torch.float32, device=dev)
+            invstd = torch.empty(c, dtype=torch.float32, device=dev)
             ws = torch.empty(int(lib.drc_bn_workspace(M, c, _sms(dev))), dtype=torch.float32, device=dev)
-            N.check(lib.drc_bn_fwd(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
-                                   _p(running_var), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), _counter(dev).data_ptr(),
-                                   M, c, float(eps), float(momentum), int(relu), _sms(dev), _coop(),
-                                   torch.cuda.current_stream().cuda_stream), "bn_fwd")
+            ws_ptr = ws.data_ptr()
+        N.check(lib.drc_bn_fwd(x.data_ptr(), _p(residual), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
+                               _p(running_var), mean.data_ptr(), invstd.data_ptr(), ws_ptr, _counter(dev).data_ptr(),
+                               M, c, float(eps), float(momentum), int(relu), _sms(dev), int(have_stats),
+                               torch.cuda.current_stream().cuda_stream), "bn_fwd")
         ctx.save_for_backward(x, y if relu else None, gamma, mean, invstd)
         ctx.relu, ctx.has_res = bool(relu), residual is not None
         return y
@@ -151,31 +131,42 @@ class _BnActFn(torch.autograd.Function):
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
         torch.cuda.set_device(dev)
-        if getattr(ctx, "cluster", False):
-            N.check(lib.drc_bn_bwd_cluster(dy.data_ptr(), _p(y), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                                           dx.data_ptr(), _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), M, c, int(ctx.relu),
-                                           torch.cuda.current_stream().cuda_stream), "bn_bwd_cluster")
-            return dx, dres, dgamma, dbeta, None, None, None, None, None
         sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
         ws = torch.empty(int(lib.drc_bn_workspace(M, c, _sms(dev))), dtype=torch.float32, device=dev)
         N.check(lib.drc_bn_bwd(dy.data_ptr(), _p(y), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                                dx.data_ptr(), _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), sums.data_ptr(),
-                               _counter(dev)[8:].data_ptr(), M, c, int(ctx.relu), _sms(dev), _coop(),
+                               _counter(dev)[8:].data_ptr(), M, c, int(ctx.relu), _sms(dev),
                                torch.cuda.current_stream().cuda_stream), "bn_bwd")
-        return dx, dres, dgamma, dbeta, None, None, None, None, None
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 class FusedBatchNorm2d(nn.BatchNorm2d):
-    """``nn.BatchNorm2d`` + optional fused residual add and ReLU."""
+    """``nn.BatchNorm2d`` + optional fused residual add and ReLU.  When the producing ``ops.conv.Conv2d`` was called with
+    ``bn=self`` its epilogue already computed this layer's batch statistics (``pending_stats``) and only the apply kernel runs."""
 
     def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, relu: bool = False):
         super().__init__(num_features, eps=eps, momentum=momentum)
         self.fuse_relu = relu
+        self.pending_stats = None
+
+    def _fused_ok(self, x: torch.Tensor) -> bool:
+        return self.weight.dtype == torch.float32 and self.track_running_stats and fused_supported(x, self.training)
+
+    def stat_request(self, x_in: torch.Tensor, channels: int):
+        """Called by the producing convolution: a BnStatRequest if this layer will take the fused path for its output."""
+        from .conv import BnStatRequest
+        if not (self.training and self.weight.dtype == torch.float32 and self.track_running_stats and channels == self.num_features
+                and channels <= 512 and os.environ.get("DRACO_BN", "fused") == "fused"
+                and os.environ.get("DRACO_BN_STATS", "conv") == "conv" and bool(_lib().drc_bn_supported(channels))):
+            return None
+        upd = UPDATE_RUNNING_STATS
+        return BnStatRequest(self.eps, self.momentum if self.momentum is not None else 0.1,
+                             self.running_mean if upd else None, self.running_var if upd else None)
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: Optional[bool] = None) -> torch.Tensor:
         relu = self.fuse_relu if relu is None else relu
-        if (self.weight.dtype == torch.float32 and self.track_running_stats and fused_supported(x, self.training)
-                and (residual is None or residual.shape == x.shape)):
+        pend, self.pending_stats = self.pending_stats, None
+        if self._fused_ok(x) and (residual is None or residual.shape == x.shape):
             backend_counters["fused"] += 1
             upd = UPDATE_RUNNING_STATS
             if upd and self.num_batches_tracked is not None:
@@ -183,9 +174,14 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
                     _pending_counts.append(self.num_batches_tracked)
                 else:
                     self.num_batches_tracked.add_(1)
+            mean = invstd = None
+            if pend is not None and pend[0] is x:
+                mean, invstd = pend[1], pend[2]                   # running statistics were updated by the convolution
+                backend_counters["conv_stats"] = backend_counters.get("conv_stats", 0) + 1
             return _BnActFn.apply(x, residual, self.weight, self.bias, self.running_mean if upd else None,
                                   self.running_var if upd else None, self.eps,
-                                  self.momentum if self.momentum is not None else 0.1, relu)
+                                  self.momentum if self.momentum is not None else 0.1, relu, mean, invstd)
+        assert pend is None, "a convolution produced fused statistics for a BatchNorm call that cannot use them"
         backend_counters["aten"] += 1
         if self.training and not UPDATE_RUNNING_STATS:
             y = F.batch_norm(x, None, None, self.weight, self.bias, True, 0.0, self.eps)

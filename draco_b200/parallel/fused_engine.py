@@ -228,7 +228,6 @@ class FusedEngine:
                 main = torch.cuda.current_stream()
                 fork = torch.cuda.Event()
                 fork.record(main)
-                _norm.FORCE_COOP = 0
                 try:
                     for i, w in enumerate(order):
                         st, pst = self.worker_streams[i % len(self.worker_streams)]
@@ -238,21 +237,14 @@ class FusedEngine:
                         with torch.cuda.stream(st):
                             n += self._enqueue_worker(w, step_host, pst)
                 finally:
-                    _norm.FORCE_COOP = None
                     _norm.UPDATE_RUNNING_STATS = True
                 for st, _ in self.worker_streams[: len(order)]:
                     main.wait_stream(st)
             else:
-                from ..ops import norm as _norm
-                # Replicas of a vote group may live on different GPUs: every rank must run the SAME BatchNorm variant or their
-                # gradients stop being bit-identical.  If any rank of the job runs its workers on concurrent streams (which
-                # forces the two-kernel form), this rank uses the two-kernel form too.
-                _norm.FORCE_COOP = 0 if self.job_uses_worker_streams else None
-                try:
-                    for w in order:
-                        n += self._enqueue_worker(w, step_host, self.push_stream)
-                finally:
-                    _norm.FORCE_COOP = None
+                # (every rank runs the same kernels whatever its stream layout: replicas of a vote group on different GPUs
+                # stay bit-identical)
+                for w in order:
+                    n += self._enqueue_worker(w, step_host, self.push_stream)
         if self.local_workers:
             comp_phase.__exit__(None, None, None)
             nvtx.range_pop()

@@ -212,7 +212,7 @@ class WorkerCompute:
 
     # ------------------------------------------------------------------ compute
     def _prep_input(self, x_u8: torch.Tensor) -> torch.Tensor:
-        if (os.environ.get("DRACO_FUSED_PREP", "0") == "1" and x_u8.is_cuda and x_u8.dim() == 4 and x_u8.shape[1] <= 4
+        if (os.environ.get("DRACO_FUSED_PREP", "1") == "1" and x_u8.is_cuda and x_u8.dim() == 4 and x_u8.shape[1] <= 4
                 and x_u8.is_contiguous() and self.channels_last):
             return self._prep_input_fused(x_u8)
         x = (x_u8.float().div_(255.0).sub_(self._mean)).div_(self._std)

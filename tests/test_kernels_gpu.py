@@ -367,10 +367,7 @@ def test_cross_stream_flag_handshake(K, dev):
     assert err.item() == 0 and torch.equal(out, g32)
 
 
-@pytest.mark.timeout(120)       # a never-run kernel that hangs must not eat the GPU budget
-@pytest.mark.skipif(__import__("os").environ.get("DRACO_EXPERIMENTAL", "0") != "1",
-                    reason="loss_fused.cu has not run on hardware yet (written after the round's GPU budget was spent); "
-                           "set DRACO_EXPERIMENTAL=1")
+@pytest.mark.timeout(120)
 def test_fused_cross_entropy_kernel(monkeypatch):
     """One-launch softmax-CE + gradient + Prec@k (csrc/cuda/loss_fused.cu) vs the PyTorch ops it replaces."""
     import torch.nn.functional as F
@@ -406,9 +403,7 @@ def test_fused_cross_entropy_kernel(monkeypatch):
         assert torch.equal(l2.grad, l3.grad)
 
 
-@pytest.mark.timeout(120)       # a never-run kernel that hangs must not eat the GPU budget
-@pytest.mark.skipif(__import__("os").environ.get("DRACO_EXPERIMENTAL", "0") != "1",
-                    reason="prep_input.cu has not run on hardware yet; set DRACO_EXPERIMENTAL=1")
+@pytest.mark.timeout(120)
 def test_fused_input_prep_kernel(monkeypatch):
     from draco_b200 import JobConfig
     from draco_b200.data import synthetic_dataset
@@ -426,5 +421,6 @@ def test_fused_input_prep_kernel(monkeypatch):
         ref = wc._prep_input(x)
         monkeypatch.setenv("DRACO_FUSED_PREP", "1")
         got = wc._prep_input(x)
-        assert got.shape == ref.shape and got.dtype == ref.dtype and got.stride() == ref.stride()
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        assert got.is_contiguous(memory_format=torch.channels_last) and ref.is_contiguous(memory_format=torch.channels_last)
         assert float((got.float() - ref.float()).abs().max()) <= 2e-2          # at most one bf16 ulp of a value ~2.6

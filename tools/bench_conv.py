@@ -1,5 +1,7 @@
-"""3x3 convolution: tcgen05 TMA-patch implicit GEMM (ours) vs cuDNN, ResNet-18/CIFAR shapes at B=128 (CUDA events, warm L2 as
-in the real step: the activation was just produced by the previous layer)."""
+"""Per-layer micro-benchmark of the convolution / BatchNorm kernels against the library (cuDNN / ATen) on the ResNet-18/CIFAR
+shapes at B=128.  Every op is captured TEN times back to back in a CUDA graph and the graph replay is timed with CUDA events
+(device time per launch; no Python / ctypes / tensor-map-encode time in the number, L2-warm as in the real step where the
+activation was just produced by the previous layer).  Writes gpurun_out/conv_bench.json."""
 import json
 import os
 import sys
@@ -8,70 +10,116 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from draco_b200.ops.conv import conv3x3_tcgen05, conv3x3_wgrad_tcgen05  # noqa: E402
+from draco_b200.ops import conv as C  # noqa: E402
+from draco_b200.ops import norm as NM  # noqa: E402
 
 torch.backends.cudnn.deterministic = True
 torch.backends.cudnn.benchmark = False
 dev = torch.device("cuda", 0)
+REP = 10
 
 
-def timeit(fn, iters=20, warm=5):
-    for _ in range(warm):
+def timeit(fn, replays=8):
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(REP):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(replays):
+        g.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e3          # us
+    return round(s.elapsed_time(e) / (replays * REP) * 1e3, 2)          # us per launch
+
+
+def cl(t):
+    return t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def wt(k, c, ks):
+    return (torch.randn(k, c, ks, ks, device=dev) * 0.05).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
 
 
 rows = []
-for (n, c, k, hw) in [(128, 64, 64, 32), (128, 128, 128, 16), (128, 256, 256, 8), (128, 512, 512, 4), (128, 64, 128, 16)]:
-    x = torch.randn(n, c, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    w = (torch.randn(k, c, 3, 3, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    dy = torch.randn(n, k, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    fl = 2.0 * n * hw * hw * k * c * 9
-    t_f = timeit(lambda: conv3x3_tcgen05(x, w))
-    t_fc = timeit(lambda: F.conv2d(x, w, padding=1))
-    t_d = timeit(lambda: conv3x3_tcgen05(dy, w, True))
-    t_dc = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False]))
-    t_w = timeit(lambda: conv3x3_wgrad_tcgen05(dy, x))
-    t_wc = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False]))
-    rows.append({"wgrad_us": t_w, "cudnn_wgrad_us": t_wc, "N": n, "Cin": c, "Cout": k, "HW": hw, "fprop_us": t_f, "cudnn_fprop_us": t_fc, "dgrad_us": t_d, "cudnn_dgrad_us": t_dc,
-                 "fprop_tflops": fl / t_f / 1e6, "cudnn_fprop_tflops": fl / t_fc / 1e6})
-    print(rows[-1], flush=True)
-if os.environ.get("DRACO_EXPERIMENTAL", "0") == "1":
-    # halo-reuse kernels on the 64 -> 64 layer1 shape vs the per-tap kernel and cuDNN
-    from draco_b200.ops.conv import conv3x3_halo  # noqa: E402
-    try:
-        x = torch.randn(128, 64, 32, 32, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        w = (torch.randn(64, 64, 3, 3, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        row = {"shape": "128x64x32x32 -> 64", "halo_fprop_us": timeit(lambda: conv3x3_halo(x, w)),
-               "halo_dgrad_us": timeit(lambda: conv3x3_halo(x, w, True)), "tap_fprop_us": timeit(lambda: conv3x3_tcgen05(x, w)),
-               "cudnn_fprop_us": timeit(lambda: F.conv2d(x, w, padding=1))}
-        rows.append(row)
-        print(row, flush=True)
-    except Exception as e:  # noqa: BLE001  (keep the rest of the bench alive)
-        print("halo bench failed:", e, flush=True)
-    # strided / 1x1 layers of ResNet-18 on the tap-table kernels vs cuDNN (the stride-2 dgrads are cuDNN's slowest kernels here)
-    from draco_b200.ops.conv import convg_tcgen05, convg_wgrad_tcgen05  # noqa: E402
-    for (n, c, k, hw, ks) in [(128, 64, 128, 32, 3), (128, 128, 256, 16, 3), (128, 256, 512, 8, 3), (128, 64, 128, 32, 1),
-                              (128, 128, 256, 16, 1), (128, 256, 512, 8, 1)]:
-        pad = ks // 2
-        x = torch.randn(n, c, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        w = (torch.randn(k, c, ks, ks, device=dev) * 0.05).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
-        dy = torch.randn(n, k, hw // 2, hw // 2, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        args = (None, [2, 2], [pad, pad], [1, 1], False, [0, 0], 1)
-        row = {"N": n, "Cin": c, "Cout": k, "HW": hw, "ks": ks, "stride": 2,
-               "fprop_us": timeit(lambda: convg_tcgen05(x, w, (hw, hw), 2)),
-               "cudnn_fprop_us": timeit(lambda: F.conv2d(x, w, stride=2, padding=pad)),
-               "dgrad_us": timeit(lambda: convg_tcgen05(dy, w, (hw, hw), 2, True)),
-               "cudnn_dgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [True, False, False])),
-               "wgrad_us": timeit(lambda: convg_wgrad_tcgen05(dy, x, ks, 2)),
-               "cudnn_wgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [False, True, False]))}
-        rows.append(row)
-        print(row, flush=True)
+N = int(os.environ.get("BENCH_BATCH", "128"))
+shapes = [(64, 64, 32, 3, 1), (128, 128, 16, 3, 1), (256, 256, 8, 3, 1), (512, 512, 4, 3, 1),
+          (64, 128, 32, 3, 2), (128, 256, 16, 3, 2), (256, 512, 8, 3, 2),
+          (64, 128, 32, 1, 2), (128, 256, 16, 1, 2), (256, 512, 8, 1, 2)]
+for (c, k, hw, ks, st) in shapes:
+    pad = ks // 2
+    x = cl(torch.randn(N, c, hw, hw, device=dev))
+    w = wt(k, c, ks)
+    dy = cl(torch.randn(N, k, hw // st, hw // st, device=dev))
+    args = (None, [st, st], [pad, pad], [1, 1], False, [0, 0], 1)
+    halo = ks == 3 and st == 1 and C.halo_supported(hw, hw, c, k)
+    req = C.BnStatRequest(1e-5, 0.1)
+    if halo:
+        f = lambda: C.conv3x3_halo(x, w)                                  # noqa: E731
+        fs = lambda: C.conv3x3_halo(x, w, False, None, req)               # noqa: E731
+        d = lambda: C.conv3x3_halo(dy, w, True)                           # noqa: E731
+    else:
+        f = lambda: C.convg_tcgen05(x, w, (hw, hw), st)                   # noqa: E731
+        fs = lambda: C.convg_tcgen05(x, w, (hw, hw), st, False, None, req)  # noqa: E731
+        d = lambda: C.convg_tcgen05(dy, w, (hw, hw), st, True)            # noqa: E731
+    row = {"Cin": c, "Cout": k, "HW": hw, "ks": ks, "stride": st, "kernel": "halo" if halo else "tap",
+           "fprop_us": timeit(f), "fprop_bnstats_us": timeit(fs),
+           "cudnn_fprop_us": timeit(lambda: F.conv2d(x, w, stride=st, padding=pad)),
+           "dgrad_us": timeit(d),
+           "cudnn_dgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [True, False, False])),
+           "wgrad_us": timeit(lambda: C.convg_wgrad_tcgen05(dy, x, ks, st)),
+           "cudnn_wgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [False, True, False]))}
+    if halo:
+        row["tap_fprop_us"] = timeit(lambda: C.convg_tcgen05(x, w, (hw, hw), st))
+    fl = 2.0 * N * (hw // st) ** 2 * k * c * ks * ks
+    row["fprop_tflops"] = round(fl / row["fprop_us"] / 1e6, 1)
+    rows.append(row)
+    print(row, flush=True)
+
+# stem
+x = cl(torch.randn(N, 3, 32, 32, device=dev))
+w = wt(64, 3, 3)
+dy = cl(torch.randn(N, 64, 32, 32, device=dev))
+args = (None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1)
+req = C.BnStatRequest(1e-5, 0.1)
+row = {"layer": "stem 3->64 32x32", "fprop_us": timeit(lambda: C.conv_stem_fprop(x, w)),
+       "fprop_bnstats_us": timeit(lambda: C.conv_stem_fprop(x, w, None, req)),
+       "cudnn_fprop_us": timeit(lambda: F.conv2d(x, w, padding=1)),
+       "wgrad_us": timeit(lambda: C.conv_stem_wgrad(dy, x)),
+       "cudnn_wgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [False, True, False]))}
+rows.append(row)
+print(row, flush=True)
+
+# BatchNorm (+ReLU): forward with / without given statistics, backward; vs ATen batch_norm + relu
+for (c, hw) in [(64, 32), (128, 16), (256, 8), (512, 4)]:
+    x = cl(torch.randn(N, c, hw, hw, device=dev))
+    gy = cl(torch.randn(N, c, hw, hw, device=dev))
+    bn = NM.FusedBatchNorm2d(c).to(dev)
+    mean, invstd = x.float().mean((0, 2, 3)), (x.float().var((0, 2, 3), unbiased=False) + 1e-5).rsqrt()
+    xg = x.clone().requires_grad_(True)
+    y = bn(xg, relu=True)
+
+    def fwd_given():
+        return NM._BnActFn.apply(x, None, bn.weight, bn.bias, None, None, 1e-5, 0.1, True, mean, invstd)
+
+    def fwd_full():
+        return NM._BnActFn.apply(x, None, bn.weight, bn.bias, None, None, 1e-5, 0.1, True, None, None)
+
+    def bwd():
+        return torch.autograd.grad(y, xg, gy, retain_graph=True)
+
+    xa = x.clone().requires_grad_(True)
+    ya = F.relu(F.batch_norm(xa, None, None, bn.weight, bn.bias, True, 0.1, 1e-5))
+    row = {"layer": f"bn+relu C={c} {hw}x{hw}", "MB": round(x.numel() * 2 / 1e6, 1), "fwd_apply_only_us": timeit(fwd_given),
+           "fwd_stats_apply_us": timeit(fwd_full), "bwd_us": timeit(bwd),
+           "aten_fwd_us": timeit(lambda: F.relu(F.batch_norm(x, None, None, bn.weight, bn.bias, True, 0.1, 1e-5))),
+           "aten_bwd_us": timeit(lambda: torch.autograd.grad(ya, xa, gy, retain_graph=True))}
+    rows.append(row)
+    print(row, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/conv_bench.json", "w"), indent=1)

@@ -22,14 +22,12 @@ for s in $STAGES; do
     worker) timeout -k 10 600 python tools/bench_worker.py > gpurun_out/bench_worker.log 2>&1; echo "worker rc=$?" ;;
     diag) timeout -k 10 120 python tools/diag_flags.py > gpurun_out/diag_flags.log 2>&1; echo "diag rc=$?" ;;
     norm) timeout -k 10 300 python -m pytest tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/t_norm.log 2>&1; echo "norm rc=$?" ;;
-    convbench) timeout -k 10 300 python tools/bench_conv.py > gpurun_out/conv_bench.log 2>&1; echo "convbench rc=$?" ;;
-    ncu_conv) timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"conv3x3|wgrad_reduce" -s 8 -c 8 -f -o gpurun_out/prof_conv python tools/prof_conv.py > gpurun_out/ncu_conv.log 2>&1; echo "ncu_conv rc=$?" ;;
+    convbench) timeout -k 10 420 python tools/bench_conv.py > gpurun_out/conv_bench.log 2>&1; echo "convbench rc=$?" ;;
+    conv) timeout -k 10 600 python -m pytest tests/test_gemm_gpu.py tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider -x -k "conv or bn or norm" > gpurun_out/t_conv.log 2>&1; echo "conv rc=$?" ;;
+    ncu_conv) timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"convg|conv_halo|wgradg|stem_|bn_" -s 0 -c 60 -f -o gpurun_out/prof_conv python tools/prof_conv.py > gpurun_out/ncu_conv.log 2>&1; echo "ncu_conv rc=$?" ;;
     sanitizer) for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do timeout -k 10 420 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider -x -k "push or vote or aggregate or geometric or krum or cyclic" > gpurun_out/sanitizer_$tool.log 2>&1; echo "sanitizer $tool rc=$?"; done ;;
     geomed) timeout -k 10 300 python -m pytest tests/test_kernels_gpu.py tests/test_fused_engine_gpu.py -q -m gpu -p no:cacheprovider -k "geomed or krum or geometric" > gpurun_out/t_geomed.log 2>&1; echo "geomed rc=$?"
             timeout -k 10 300 python bench.py --gpus 1 --steps 30 --warmup 5 --approach baseline --mode geometric_median > gpurun_out/bench1_geomed.log 2>&1; echo "bench geomed rc=$?" ;;
-    experimental) DRACO_EXPERIMENTAL=1 timeout -k 10 420 python -m pytest tests/test_gemm_gpu.py tests/test_kernels_gpu.py tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider -k "convg or conv_stem or fused_cross_entropy or fused_input_prep or cluster_bn or halo_reuse" > gpurun_out/t_experimental.log 2>&1; echo "experimental rc=$?"
-                  DRACO_EXPERIMENTAL=1 timeout -k 10 300 python tools/bench_conv.py > gpurun_out/conv_bench_strided.log 2>&1; echo "convbench(strided) rc=$?" ;;
-    worker_native) PROFILE_TAG=_native DRACO_CONV3X3=tcgen05 DRACO_CONV_STRIDED=tcgen05 DRACO_CONV_STEM=native DRACO_FUSED_LOSS=1 DRACO_FUSED_PREP=1 DRACO_BN_CLUSTER=1 timeout -k 10 600 python tools/bench_worker.py > gpurun_out/bench_worker_native.log 2>&1; echo "worker_native rc=$?" ;;
     alltests) timeout -k 10 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "alltests rc=$?" ;;
   esac
 done
