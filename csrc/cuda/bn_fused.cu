@@ -129,25 +129,20 @@ __device__ __forceinline__ void grid_fold(const float* partial, int C) {
   if (items4 <= BN_THREADS) {
     const int SUB = BN_THREADS / items4;
     const int item = threadIdx.x % items4, sub = threadIdx.x / items4;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sub < SUB) {
-      int g = sub;
-      for (; g + 3 * SUB < nblk; g += 4 * SUB) {
-        const float4 v0 = __ldcg(p4 + (long long)g * items4 + item), v1 = __ldcg(p4 + (long long)(g + SUB) * items4 + item);
-        const float4 v2 = __ldcg(p4 + (long long)(g + 2 * SUB) * items4 + item), v3 = __ldcg(p4 + (long long)(g + 3 * SUB) * items4 + item);
-        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
-      }
-      for (; g < nblk; g += SUB) {
-        const float4 v0 = __ldcg(p4 + (long long)g * items4 + item);
-        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      constexpr int FB = 16;                                        // independent 16-byte loads in flight
+      for (int g0 = sub; g0 < nblk; g0 += FB * SUB) {
+        float4 v[FB];
+#pragma unroll
+        for (int u = 0; u < FB; ++u) {
+          const int g = g0 + u * SUB;
+          v[u] = g < nblk ? __ldcg(p4 + (long long)g * items4 + item) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < FB; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }    // fixed order
       }
     }
-    float4 t;
-    t.x = (a0.x + a1.x) + (a2.x + a3.x); t.y = (a0.y + a1.y) + (a2.y + a3.y);
-    t.z = (a0.z + a1.z) + (a2.z + a3.z); t.w = (a0.w + a1.w) + (a2.w + a3.w);
     s4[items4 + threadIdx.x] = t;                                  // scratch behind the totals
     __syncthreads();
     if (sub == 0) {

@@ -5,9 +5,9 @@
 //      (row = pixel, 16-byte chunk j of row r at chunk j ^ (r & 7): conflict-free 16-byte stores);
 //   2. handed to ONE TMA tensor store per 64-channel half (cp.async.bulk.tensor...global.shared::cta, SASS UTMASTG) -- the
 //      4-D box mirrors the load box, so partial batches are clipped by the TMA unit and every global write is a full line;
-//   3. (optional) reduced per channel for the BatchNorm that follows the convolution: every epilogue thread owns one channel
-//      (x one row range) of the staged bf16 tile and accumulates sum / sum-of-squares into shared-memory accumulators that live
-//      for the whole persistent CTA.  At kernel end each CTA writes its partial [2][C] to a workspace slot and the LAST CTA
+//   3. (optional) reduced per channel for the BatchNorm that follows the convolution: every epilogue thread owns 8 channels
+//      (x one row set) of the staged bf16 tile and accumulates sum / sum-of-squares in registers across the tiles of the
+//      persistent CTA (flushed into per-warp shared-memory accumulators).  At kernel end each CTA writes its partial [2][C] to a workspace slot and the LAST CTA
 //      (atomic ticket) folds the slots in a fixed order with 16-byte loads and finalises mean / invstd / running statistics:
 //      the statistics pass of the BatchNorm (one full read of the activation + one launch per layer) disappears.
 //
@@ -37,7 +37,7 @@ struct BnStatArgs {
 
 // shared-memory bytes the epilogue needs: staging tile + statistics accumulators
 __host__ __device__ constexpr int staging_bytes(int block_n) { return block_n * 128 * 2; }          // 128 rows x block_n bf16
-__host__ __device__ constexpr int stat_bytes() { return 2 * 2 * STAT_MAX_C * 4; }                   // [parts <= 2][2][512] fp32
+__host__ __device__ constexpr int stat_bytes() { return 4 * 2 * STAT_MAX_C * 4; }                   // [4 warps][2][512] fp32
 
 // Drain one accumulator tile.  Called by all 128 epilogue threads (et = 0..127 = tile row).
 //   tmem_acc : TMEM address of column 0 of this accumulator (lane field 0)
@@ -81,28 +81,56 @@ __device__ __forceinline__ void drain_tile(uint32_t tmem_acc, uint8_t* sbuf, flo
   (void)valid_rows; (void)s_stat;
 }
 
-// per-channel sum / sum of squares of the staged (bf16-rounded) tile
+// Per-channel sum / sum of squares of the staged (bf16-rounded) tiles, kept in REGISTERS across the tiles of a CTA: epilogue
+// thread et owns the 16-byte chunk (8 channels) j = et & 7 of every 64-channel half and the rows rg, rg + 16, ... (rg = et >> 3),
+// i.e. eight 16-byte shared-memory loads per half per tile (conflict-free: a quarter warp reads one 128-byte row).
 template <int BLOCK_N>
-__device__ __forceinline__ void accumulate_stats(const uint8_t* sbuf, float* s_stat, int et, int valid_rows, int col0, int Cn) {
-  constexpr int PARTS = EPI_THREADS / BLOCK_N;                     // 2 (BLOCK_N = 64) or 1 (128)
-  constexpr int ROWS = 128 / PARTS;
-  const int ch = et % BLOCK_N, part = et / BLOCK_N;
-  if (col0 + ch >= Cn) return;
-  const uint8_t* base = sbuf + (ch >> 6) * (128 * 128) + (ch & 7) * 2;
-  const int lc = (ch & 63) >> 3;
-  float s = 0.f, qq = 0.f;
-  const int r0 = part * ROWS;
-  int r1 = r0 + ROWS; if (r1 > valid_rows) r1 = valid_rows;
-#pragma unroll 8
-  for (int r = r0; r < r1; ++r) {
-    const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + r * 128 + ((lc ^ (r & 7)) << 4)));
-    s += v;
-    qq = fmaf(v, v, qq);
+struct StatAcc {
+  float s[BLOCK_N / 8], q[BLOCK_N / 8];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < BLOCK_N / 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   }
-  float* acc = s_stat + (part * 2) * STAT_MAX_C + col0 + ch;       // slot owned by exactly this thread for this tile
-  acc[0] += s;
-  acc[STAT_MAX_C] += qq;
-}
+  __device__ __forceinline__ void add_tile(const uint8_t* sbuf, int et, int valid_rows) {
+    const int j = et & 7, rg = et >> 3;
+#pragma unroll
+    for (int box = 0; box < BLOCK_N / 64; ++box) {
+      const uint8_t* base = sbuf + box * (128 * 128);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rg + 16 * i;
+        if (r < valid_rows) {
+          const uint4 v = *reinterpret_cast<const uint4*>(base + r * 128 + ((j ^ (r & 7)) << 4));
+          const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(p[e]);
+            s[box * 8 + 2 * e] += f.x;          q[box * 8 + 2 * e] = fmaf(f.x, f.x, q[box * 8 + 2 * e]);
+            s[box * 8 + 2 * e + 1] += f.y;      q[box * 8 + 2 * e + 1] = fmaf(f.y, f.y, q[box * 8 + 2 * e + 1]);
+          }
+        }
+      }
+    }
+  }
+  // fold the four row groups of a warp (fixed xor tree) and add to this warp's shared-memory accumulators [warp][2][C]
+  __device__ __forceinline__ void flush(float* s_stat, int et, int col0, int Cn) {
+    const int j = et & 7, warp = et >> 5;
+#pragma unroll
+    for (int i = 0; i < BLOCK_N / 8; ++i) {
+      float a = s[i], b = q[i];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+      const int c = col0 + (i >> 3) * 64 + j * 8 + (i & 7);
+      if ((et & 31) < 8 && c < Cn) {
+        float* acc = s_stat + (warp * 2) * STAT_MAX_C + c;
+        acc[0] += a;
+        acc[STAT_MAX_C] += b;
+      }
+    }
+    clear();
+  }
+};
+constexpr int STAT_PARTS = 4;             // one accumulator row per epilogue warp
 
 // Kernel tail, executed by ALL threads of the CTA after the role loops joined (__syncthreads before the call).
 //   slot / nslots: workspace row of this CTA / number of rows the last CTA folds
@@ -134,27 +162,20 @@ __device__ __forceinline__ void finalize_stats(const BnStatArgs& st, float* s_st
   for (int i0 = 0; i0 < items4; i0 += NUM_THREADS) {                 // one pass unless 2C/4 > NUM_THREADS
     const int item = i0 + (int)threadIdx.x % (items4 < NUM_THREADS ? items4 : NUM_THREADS);
     const int sub = items4 < NUM_THREADS ? (int)threadIdx.x / items4 : 0;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sub < SUB && item < items4) {
-      int g = sub;
-      for (; g + 3 * SUB < nslots; g += 4 * SUB) {
-        const float4 v0 = __ldcg(p4 + (long long)g * items4 + item);
-        const float4 v1 = __ldcg(p4 + (long long)(g + SUB) * items4 + item);
-        const float4 v2 = __ldcg(p4 + (long long)(g + 2 * SUB) * items4 + item);
-        const float4 v3 = __ldcg(p4 + (long long)(g + 3 * SUB) * items4 + item);
-        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
-      }
-      for (; g < nslots; g += SUB) {
-        const float4 v0 = __ldcg(p4 + (long long)g * items4 + item);
-        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      constexpr int FB = 16;                                          // independent 16-byte loads in flight
+      for (int g0 = sub; g0 < nslots; g0 += FB * SUB) {
+        float4 v[FB];
+#pragma unroll
+        for (int u = 0; u < FB; ++u) {
+          const int g = g0 + u * SUB;
+          v[u] = g < nslots ? __ldcg(p4 + (long long)g * items4 + item) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < FB; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }      // fixed order
       }
     }
-    float4 t;
-    t.x = (a0.x + a1.x) + (a2.x + a3.x); t.y = (a0.y + a1.y) + (a2.y + a3.y);
-    t.z = (a0.z + a1.z) + (a2.z + a3.z); t.w = (a0.w + a1.w) + (a2.w + a3.w);
     __syncthreads();
     reinterpret_cast<float4*>(s_scratch)[threadIdx.x] = t;
     __syncthreads();

@@ -83,7 +83,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_base_slot);
   if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < 4 * convepi::STAT_MAX_C; i += convepi::EPI_THREADS) s_stat[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < 2 * convepi::STAT_PARTS * convepi::STAT_MAX_C; i += convepi::EPI_THREADS) s_stat[i] = 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -143,6 +143,8 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     // ===================== epilogue: staged TMA store (+ BatchNorm statistics) =====================
     const int et = threadIdx.x - 128;
     int acc = 0; uint32_t acc_phase = 0;
+    convepi::StatAcc<BLOCK_N> sacc;
+    sacc.clear();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int w0 = (tile % wt) * TW, h0 = ((tile / wt) % ht) * TH, n0 = tile / (wt * ht);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -153,9 +155,10 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         tma_store_4d(&tmap_out, sbuf, 0, w0, h0, n0);
         tma_store_commit();
       }
-      if (want_stats) convepi::accumulate_stats<BLOCK_N>(sbuf, s_stat, et, BLOCK_M, 0, BLOCK_N);
+      if (want_stats) sacc.add_tile(sbuf, et, BLOCK_M);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (want_stats) sacc.flush(s_stat, et, 0, BLOCK_N);
     if (et == 0) tma_store_wait<0>();
   }
 
@@ -163,7 +166,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
   if (want_stats)
-    convepi::finalize_stats<NUM_THREADS>(a.stat, s_stat, convepi::EPI_THREADS / BLOCK_N, BLOCK_N, (int)blockIdx.x, (int)gridDim.x, 0,
+    convepi::finalize_stats<NUM_THREADS>(a.stat, s_stat, convepi::STAT_PARTS, BLOCK_N, (int)blockIdx.x, (int)gridDim.x, 0,
                                          BLOCK_N, reinterpret_cast<float*>(sbuf));
 }
 

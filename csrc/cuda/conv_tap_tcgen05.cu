@@ -94,7 +94,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_base_slot);
   if (TMA_EPI && warp >= 4) {
-    for (int i = threadIdx.x - 128; i < 4 * convepi::STAT_MAX_C; i += convepi::EPI_THREADS) s_stat[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < 2 * convepi::STAT_PARTS * convepi::STAT_MAX_C; i += convepi::EPI_THREADS) s_stat[i] = 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -161,6 +161,11 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int q = warp & 3;
     const int et = threadIdx.x - 128;
     int acc = 0; uint32_t acc_phase = 0;
+    convepi::StatAcc<BLOCK_N> sacc;
+    sacc.clear();
+    // every tile of this CTA covers the same channels (one N tile, or one tile per CTA): statistics stay in registers until the end
+    const bool stat_keep = n_tiles == 1 || num_tiles <= (int)gridDim.x;
+    int stat_col0 = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / n_tiles, n0 = (tile % n_tiles) * BLOCK_N;
       const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
@@ -177,7 +182,11 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             if (n0 + 64 * j < a.Cn) tma_store_4d(&tmap_out, sbuf + j * (128 * 128), n0 + 64 * j, w0, h0, nb0);
           tma_store_commit();
         }
-        if (want_stats) convepi::accumulate_stats<BLOCK_N>(sbuf, s_stat, et, valid_rows, n0, a.Cn);
+        if (want_stats) {
+          sacc.add_tile(sbuf, et, valid_rows);
+          stat_col0 = n0;
+          if (!stat_keep) sacc.flush(s_stat, et, n0, a.Cn);
+        }
       } else {
         const int m = q * 32 + lane;                             // row of the tile = pixel of the patch (w fastest)
         const int pw = w0 + m % a.BW, ph = h0 + (m / a.BW) % a.BH, pn = nb0 + m / (a.BW * a.BH);
@@ -213,6 +222,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (want_stats && stat_keep) sacc.flush(s_stat, et, stat_col0, a.Cn);
     if (TMA_EPI && et == 0) tma_store_wait<0>();                 // every tile of this CTA is in global memory
   }
 
@@ -224,7 +234,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const bool one_tile = num_tiles <= (int)gridDim.x;
     const int mt = blockIdx.x / n_tiles, n0 = (blockIdx.x % n_tiles) * BLOCK_N;
     const int c_hi = n0 + BLOCK_N < a.Cn ? n0 + BLOCK_N : a.Cn;
-    convepi::finalize_stats<NUM_THREADS>(a.stat, s_stat, convepi::EPI_THREADS / BLOCK_N, a.Cn, one_tile ? mt : (int)blockIdx.x,
+    convepi::finalize_stats<NUM_THREADS>(a.stat, s_stat, convepi::STAT_PARTS, a.Cn, one_tile ? mt : (int)blockIdx.x,
                                          one_tile ? m_tiles : (int)gridDim.x, one_tile ? n0 : 0, one_tile ? c_hi : a.Cn,
                                          reinterpret_cast<float*>(sbuf));
   }

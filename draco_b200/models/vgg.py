@@ -6,9 +6,10 @@ Dropout -> Linear(512,512) -> ReLU -> Dropout -> Linear(512,512) -> ReLU -> Line
 initialised N(0, sqrt(2/(k*k*Cout))) with zero bias (vgg.py:33-38).  vgg11_bn: 38 tensors / 9,756,426
 parameters; vgg16_bn: 58 / 15,253,578.
 
-Dropout makes replicas diverge unless every holder of a batch uses the same mask: the worker runtime
-seeds the generator per (step, batch) before each forward (see parallel/worker.py), which is what makes
-VGG usable under the repetition and cyclic codes (the reference only runs VGG in the baseline approach).
+Dropout makes replicas diverge unless every holder of a batch uses the same mask: the classifier uses
+``ops.dropout.ReplicaDropout``, whose mask is a counter-based hash of (seed, step read from device memory, batch id,
+layer, element) -- identical for every holder of a batch, also inside a replayed CUDA graph.  That is what makes VGG
+usable under the repetition and cyclic codes (the reference only runs VGG in the baseline approach).
 """
 from __future__ import annotations
 
@@ -19,6 +20,7 @@ import torch
 from torch import nn
 
 from ..ops.conv import Conv2d
+from ..ops.dropout import ReplicaDropout
 from ..ops.linear import Linear
 from ..ops.norm import FusedBatchNorm2d
 from .split import make_split
@@ -72,8 +74,8 @@ class VGG(nn.Module):
         super().__init__()
         self.features = features
         self.classifier = nn.Sequential(
-            nn.Dropout(), Linear(512, 512), nn.ReLU(True),
-            nn.Dropout(), Linear(512, 512), nn.ReLU(True),
+            ReplicaDropout(salt=1), Linear(512, 512), nn.ReLU(True),
+            ReplicaDropout(salt=2), Linear(512, 512), nn.ReLU(True),
             Linear(512, num_classes),
         )
         for m in self.modules():

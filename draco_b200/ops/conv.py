@@ -215,6 +215,7 @@ class _ConvStemFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, bn_req):
         ctx.save_for_backward(x)
         ctx.has_bias = bias is not None
+        ctx.set_materialize_grads(False)          # no zero-filled "gradients" for the statistics outputs
         y = conv_stem_fprop(x, weight, bias, bn_req)
         if bn_req is not None:
             mean, invstd = bn_req.mean, bn_req.invstd
@@ -242,6 +243,7 @@ class _ConvGFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, stride, bn_req):
         ctx.save_for_backward(x, weight)
         ctx.stride, ctx.has_bias = stride, bias is not None
+        ctx.set_materialize_grads(False)          # no zero-filled "gradients" for the statistics outputs
         h, w = x.shape[2], x.shape[3]
         cout, cin, ks = weight.shape[0], weight.shape[1], weight.shape[2]
         ctx.halo = ks == 3 and stride == 1 and halo_supported(h, w, cin, cout)

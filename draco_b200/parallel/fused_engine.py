@@ -141,6 +141,7 @@ class FusedEngine:
             plan = make_plan(cfg, dataset, self.groups)
             # the PS process also builds the model: its initial parameters are the job's initial parameters
             self.worker = WorkerCompute(cfg, device, self.local_workers, plan, dataset, self.layout, self.params_f32, model)
+            self.worker.step_dev = self.step_dev       # dropout masks are keyed by the device step (graph replays advance it)
         if self.is_ps:
             self.ps = FusedPS(cfg, self.layout, device, self.params_f32, self.grad_in, self.groups, self.code)
             self.dst_ptrs = [mapA[p].ptr for p in self.place.worker_procs() if p != 0]

@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset, augment_cifar
 from ..models import build_model
+from ..ops import dropout as _dropout
 from ..ops import norm as _norm
 from ..ops.loss import accuracy, cross_entropy_with_metrics  # noqa: F401  (accuracy re-exported)
 from ..utils.metrics import wait_event
@@ -255,6 +256,19 @@ class WorkerCompute:
                 cb(b)
         return hook
 
+    def _dropout_step(self, step_host: Optional[int]):
+        """Step source of the dropout key: the engine's device step counter when there is one (``self.step_dev``, set by the
+        engine; required under graph capture), else a private device tensor refreshed from the host step, or the int on CPU."""
+        if self.device.type != "cuda":
+            return int(step_host or 1)
+        if getattr(self, "step_dev", None) is not None:
+            return self.step_dev
+        assert step_host is not None, "dropout under graph capture needs the engine's device step counter"
+        if getattr(self, "_step_priv", None) is None:
+            self._step_priv = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._step_priv.fill_(int(step_host))
+        return self._step_priv
+
     def forward_backward(self, wk: int, step_host: Optional[int] = None, on_bucket=None) -> None:
         """Run fwd/bwd for all sub-batches of logical worker ``wk``; gradients land in ``self.grads[k]``.
         Everything enqueued here is capturable in a CUDA graph (no host sync).  ``on_bucket(b)`` is called (from the
@@ -275,9 +289,10 @@ class WorkerCompute:
                 if g16 is not None:
                     g16.zero_()
                 self.binder.bind_grads(g32, g16)
-            if self.has_dropout and step_host is not None:
-                # identical dropout masks for every holder of this (step, batch)
-                torch.manual_seed((self.cfg.seed * 1000003 + step_host * 8191 + ids[k]) & 0x7FFFFFFF)
+            if self.has_dropout:
+                # identical dropout masks for every holder of this (step, batch): the mask is a hash of (seed, step, batch id, ...)
+                # and on CUDA the step is read from device memory by the kernel, so a replayed graph advances by itself
+                _dropout.set_context(self._dropout_step(step_host), self.cfg.seed, ids[k])
             x = self._prep_input(self.x_u8[wk][k])
             y = self.y[wk][k]
             with _norm.deferred_batch_counts():             # one multi-tensor kernel for all num_batches_tracked bumps
@@ -293,6 +308,8 @@ class WorkerCompute:
                     loss.backward()
             finally:
                 self._bucket_cb = None
+                if self.has_dropout:
+                    _dropout.clear_context()
             if self.zero_copy:
                 self.grad_ptrs(0, self.layout.ntensors)          # validate dtype / strides against the arena layout
                 self.grad_refs[wk][k] = [p.grad for p in self.binder.params]

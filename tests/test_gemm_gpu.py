@@ -249,7 +249,7 @@ def test_conv_layer_autograd_paths_are_native():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("n,hw", [(128, 32), (5, 32), (16, 16), (3, 64), (2, 8)])
+@pytest.mark.parametrize("n,hw", [(128, 32), (5, 32), (16, 16), (3, 64), (2, 8 * 4)])
 def test_conv_stem_native_kernels(n, hw):
     from draco_b200.ops.conv import BnStatRequest, conv_stem_fprop, conv_stem_wgrad
     dev = torch.device("cuda", 0)

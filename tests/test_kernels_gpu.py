@@ -424,3 +424,54 @@ def test_fused_input_prep_kernel(monkeypatch):
         assert got.shape == ref.shape and got.dtype == ref.dtype
         assert got.is_contiguous(memory_format=torch.channels_last) and ref.is_contiguous(memory_format=torch.channels_last)
         assert float((got.float() - ref.float()).abs().max()) <= 2e-2          # at most one bf16 ulp of a value ~2.6
+
+
+@pytest.mark.timeout(120)
+def test_replica_dropout_is_keyed_by_device_step_and_graph_safe():
+    """ops.dropout.ReplicaDropout: the mask depends only on (seed, step in DEVICE memory, batch id, layer) -- identical for two
+    "holders", different across steps / batches / layers, backward uses the forward mask, and a replayed CUDA graph follows the
+    device step without re-capture (nn.Dropout under graph replay gave every worker a different mask)."""
+    from draco_b200.ops import dropout as D
+    dev = torch.device("cuda", 0)
+    step = torch.ones(1, dtype=torch.int64, device=dev)
+    l1, l2 = D.ReplicaDropout(0.5, salt=1).to(dev), D.ReplicaDropout(0.5, salt=2).to(dev)
+    x = torch.randn(128, 512, device=dev).to(torch.bfloat16)
+
+    def run(layer, batch):
+        D.set_context(step, 428, batch)
+        xi = x.clone().requires_grad_(True)
+        y = layer(xi)
+        y.backward(torch.ones_like(y))
+        D.clear_context()
+        return y.detach(), xi.grad
+
+    ya, ga = run(l1, 3)
+    yb, gb = run(l1, 3)                                     # second holder of batch 3
+    assert torch.equal(ya, yb) and torch.equal(ga, gb)
+    keep = ya != 0
+    assert 0.4 < keep.float().mean() < 0.6
+    assert torch.equal(ga != 0, keep | (x == 0)) or torch.equal((ga != 0) & (x != 0), keep & (x != 0))   # same mask in backward
+    assert torch.allclose(ya[keep].float(), x[keep].float() * 2, rtol=1e-2)
+    assert not torch.equal(run(l1, 4)[0], ya) and not torch.equal(run(l2, 3)[0], ya)
+    # graph replay follows the device step
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    D.set_context(step, 428, 3)
+    out = torch.empty_like(x)
+    with torch.cuda.stream(side):
+        l1(x)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out.copy_(l1(x))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ya)
+    step.fill_(2)
+    g.replay()
+    torch.cuda.synchronize()
+    y2 = out.clone()
+    assert not torch.equal(y2, ya)
+    D.clear_context()
+    step.fill_(2)
+    assert torch.equal(run(l1, 3)[0], y2)

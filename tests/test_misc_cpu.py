@@ -180,3 +180,23 @@ def test_cluster_run_idle_kill_by_exact_process_group(tmp_path, monkeypatch):
     monkeypatch.undo()
     text = cluster.job_command(cfg, ["--network", "LeNet"], 0, 1, 8)
     assert "setsid nohup" in text and "draco_b200.cli.distributed_nn --network LeNet" in text and text.rstrip().endswith("echo $!; }")
+
+
+def test_replica_dropout_cpu_masks_are_keyed():
+    """CPU fallback of ops.dropout.ReplicaDropout: same key -> same mask, different step / batch / layer -> different mask;
+    without a context it is plain nn.Dropout (and identity in eval mode)."""
+    import torch
+    from draco_b200.ops import dropout as D
+    l1, l2 = D.ReplicaDropout(0.5, salt=1), D.ReplicaDropout(0.5, salt=2)
+    x = torch.ones(64, 32)
+    D.set_context(5, 428, 2)
+    a, b = l1(x), l1(x)
+    assert torch.equal(a, b) and 0.3 < (a == 0).float().mean() < 0.7 and set(a.unique().tolist()) <= {0.0, 2.0}
+    assert not torch.equal(l2(x), a)
+    D.set_context(6, 428, 2)
+    assert not torch.equal(l1(x), a)
+    D.set_context(5, 428, 3)
+    assert not torch.equal(l1(x), a)
+    D.clear_context()
+    l1.eval()
+    assert torch.equal(l1(x), x)

@@ -20,8 +20,12 @@ REP = 10
 
 
 def timeit(fn, replays=8):
-    for _ in range(3):
-        fn()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm up on a side stream (autograd + capture dislike the legacy stream)
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
@@ -110,15 +114,20 @@ for (c, hw) in [(64, 32), (128, 16), (256, 8), (512, 4)]:
     def fwd_full():
         return NM._BnActFn.apply(x, None, bn.weight, bn.bias, None, None, 1e-5, 0.1, True, None, None)
 
-    def bwd():
-        return torch.autograd.grad(y, xg, gy, retain_graph=True)
+    sy = y.detach()
 
-    xa = x.clone().requires_grad_(True)
-    ya = F.relu(F.batch_norm(xa, None, None, bn.weight, bn.bias, True, 0.1, 1e-5))
+    def bwd():                                           # the backward kernels directly (autograd's engine thread cannot be captured here)
+        return NM._BnActFn.backward(ctx_stub, gy)
+
+    class _Ctx:
+        saved_tensors = (x, sy, bn.weight, mean, invstd)
+        relu, has_res = True, False
+    ctx_stub = _Ctx()
+
     row = {"layer": f"bn+relu C={c} {hw}x{hw}", "MB": round(x.numel() * 2 / 1e6, 1), "fwd_apply_only_us": timeit(fwd_given),
            "fwd_stats_apply_us": timeit(fwd_full), "bwd_us": timeit(bwd),
            "aten_fwd_us": timeit(lambda: F.relu(F.batch_norm(x, None, None, bn.weight, bn.bias, True, 0.1, 1e-5))),
-           "aten_bwd_us": timeit(lambda: torch.autograd.grad(ya, xa, gy, retain_graph=True))}
+           }
     rows.append(row)
     print(row, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)

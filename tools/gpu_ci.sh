@@ -23,7 +23,7 @@ for s in $STAGES; do
     diag) timeout -k 10 120 python tools/diag_flags.py > gpurun_out/diag_flags.log 2>&1; echo "diag rc=$?" ;;
     norm) timeout -k 10 300 python -m pytest tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/t_norm.log 2>&1; echo "norm rc=$?" ;;
     convbench) timeout -k 10 420 python tools/bench_conv.py > gpurun_out/conv_bench.log 2>&1; echo "convbench rc=$?" ;;
-    conv) timeout -k 10 600 python -m pytest tests/test_gemm_gpu.py tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider -x -k "conv or bn or norm" > gpurun_out/t_conv.log 2>&1; echo "conv rc=$?" ;;
+    conv) timeout -k 10 600 python -m pytest tests/test_gemm_gpu.py tests/test_norm_gpu.py -q -m gpu -p no:cacheprovider -k "conv or bn or norm" > gpurun_out/t_conv.log 2>&1; echo "conv rc=$?" ;;
     ncu_conv) timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"convg|conv_halo|wgradg|stem_|bn_" -s 0 -c 60 -f -o gpurun_out/prof_conv python tools/prof_conv.py > gpurun_out/ncu_conv.log 2>&1; echo "ncu_conv rc=$?" ;;
     sanitizer) for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do timeout -k 10 420 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider -x -k "push or vote or aggregate or geometric or krum or cyclic" > gpurun_out/sanitizer_$tool.log 2>&1; echo "sanitizer $tool rc=$?"; done ;;
     geomed) timeout -k 10 300 python -m pytest tests/test_kernels_gpu.py tests/test_fused_engine_gpu.py -q -m gpu -p no:cacheprovider -k "geomed or krum or geometric" > gpurun_out/t_geomed.log 2>&1; echo "geomed rc=$?"
