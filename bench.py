@@ -16,6 +16,9 @@ every N (strong scaling): with N < 8 the logical ranks are packed onto the GPUs 
 --impl reference : the unmodified reference cannot be installed here (Python 2.7 / torch 0.3 / mpi4py, no setup.py) ->
            prints {"impl": "reference", "unavailable": ...}.
 --impl nccl      : our reference-faithful NCCL baseline (per-tensor messages, library-op decode).
+--impl nccl_flat : the honest library comparator (flat arenas, ONE broadcast + ONE message per worker, vectorised torch vote,
+           CUDA graphs, cuDNN / ATen model compute): parallel/flat_engine.py.  `vs_baseline` divides by the FASTER of the two
+           library arms recorded in baseline/measured_nccl.json.
 """
 from __future__ import annotations
 
@@ -36,7 +39,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", type=str, default="ours", choices=("ours", "reference", "nccl"))
+    ap.add_argument("--impl", type=str, default="ours", choices=("ours", "reference", "nccl", "nccl_flat"))
     ap.add_argument("--network", type=str, default="ResNet18")
     ap.add_argument("--approach", type=str, default="maj_vote")
     ap.add_argument("--mode", type=str, default="maj_vote")
@@ -51,6 +54,9 @@ def parse():
     ap.add_argument("--no-overlap-push", action="store_true")
     ap.add_argument("--push-ctas", type=int, default=16)
     ap.add_argument("--no-pipeline-ps", action="store_true")
+    ap.add_argument("--sanity-steps", type=int, default=12,
+                    help="after the timed runs: train the same job for this many steps with ONE liar (which r=3 provably tolerates) "
+                         "and with none, and report that the loss is finite and identical (0 = skip)")
     ap.add_argument("--worker-streams", type=int, default=None,
                     help="concurrent CUDA streams for logical workers sharing a GPU (default: the JobConfig default)")
     return ap.parse_args()
@@ -72,7 +78,11 @@ def main() -> int:
     if not torch.cuda.is_available():
         print(json.dumps({"metric": METRIC, "error": "no CUDA device visible"}), flush=True)
         return 1
-    transport = "nvl" if a.impl == "ours" else "nccl"
+    transport = {"ours": "nvl", "nccl": "nccl", "nccl_flat": "nccl_flat"}[a.impl]
+    if a.impl == "nccl_flat":
+        # the honest library comparator: flat arenas + one broadcast + one message per worker + CUDA graphs, and the LIBRARY
+        # compute path (cuDNN / ATen) instead of this repository's kernels (parallel/flat_engine.py)
+        os.environ.update(DRACO_CONV="cudnn", DRACO_BN="aten", DRACO_LINEAR="aten", DRACO_FUSED_LOSS="0", DRACO_FUSED_PREP="0")
     rank, world, local = init_distributed(transport)
     if world != a.gpus and rank == 0:
         print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
@@ -80,7 +90,7 @@ def main() -> int:
     cfg = JobConfig(network=a.network, dataset="Cifar10", approach=a.approach, mode=a.mode, batch_size=a.batch_size,
                     num_workers=a.num_workers, group_size=a.group_size, worker_fail=a.worker_fail, err_mode=a.err_mode,
                     lr=0.01, momentum=0.9, max_steps=total_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
-                    cuda_graphs=not a.no_cuda_graphs and a.impl == "ours", compress_grad="None", multicast=a.multicast,
+                    cuda_graphs=not a.no_cuda_graphs and a.impl in ("ours", "nccl_flat"), compress_grad="None", multicast=a.multicast,
                     synthetic_size=8192, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas,
                     pipeline_ps=not a.no_pipeline_ps,
                     **({"worker_streams": a.worker_streams} if a.worker_streams is not None else {}))
@@ -178,6 +188,36 @@ def main() -> int:
                  "worker_wait_for_params_ms_mean": sum(ww) / len(ww) if ww else None,
                  "worker_wait_for_params_ms_min": min(ww) if ww else None} if traces and any(traces) else None
     m = eng.read_metrics()
+    trainer.close()
+
+    # ------------------------------------------------------------------ sanity point: the code tolerates what it promises
+    # The headline draws 3 liars over 7 workers like the reference, so a group of 3 can be out-voted and the timed model may
+    # diverge.  Here: the SAME job with one liar per step (r = 3 tolerates 1) and with none must produce the same finite loss.
+    sanity = None
+    if a.sanity_steps > 0 and a.impl == "ours" and a.approach == "maj_vote":
+        losses = {}
+        for fails in (1, 0) if os.environ.get("DRACO_BENCH_SANITY", "1") != "0" else ():
+            c2 = JobConfig(network=a.network, dataset="Cifar10", approach=a.approach, mode=a.mode, batch_size=a.batch_size,
+                           num_workers=a.num_workers, group_size=a.group_size, worker_fail=fails, err_mode=a.err_mode if fails else "none",
+                           lr=0.01, momentum=0.9, max_steps=a.sanity_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
+                           cuda_graphs=not a.no_cuda_graphs, compress_grad="None", multicast=a.multicast, synthetic_size=8192,
+                           log_interval=10 ** 9, data_on_device=True,
+                           **({"worker_streams": a.worker_streams} if a.worker_streams is not None else {}))
+            t2 = Trainer(c2, rank=rank, world=world, device=dev, quiet=True)
+            first = None
+            for i in range(a.sanity_steps):
+                t2.train_step_async()
+                if i == 0:
+                    first = mean_loss(t2.engine.read_metrics())
+            barrier()
+            losses[fails] = (first, mean_loss(t2.engine.read_metrics()))
+            t2.close()
+    if len(locals().get("losses", {})) == 2:
+        l1, l0 = losses[1][1], losses[0][1]
+        sanity = {"steps": a.sanity_steps, "one_liar": {"loss_first": losses[1][0], "loss_last": l1},
+                  "no_liar": {"loss_first": losses[0][0], "loss_last": l0},
+                  "finite": bool(l1 is not None and l1 == l1 and abs(l1) < 1e4),
+                  "one_liar_equals_no_liar": bool(l1 is not None and l0 is not None and l1 == l0)}
 
     if rank == 0:
         value = a.steps / (ms / 1e3)
@@ -188,7 +228,9 @@ def main() -> int:
             if not headline:
                 raise LookupError("no measured baseline for this configuration")
             with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "measured_nccl.json")) as fh:
-                base = json.load(fh).get(str(world), {}).get("steps_per_s")
+                rec = json.load(fh).get(str(world), {})
+                cands = [v for v in (rec.get("steps_per_s"), rec.get("flat_steps_per_s")) if v]
+                base = max(cands) if cands else None            # the faster library arm
         except Exception:
             base = None
         out = {
@@ -207,7 +249,7 @@ def main() -> int:
                        "note": ("adversaries are drawn over all workers each step like the reference (src/util.py:100-103), so "
                                 "with r=3 and 3 liars a group can be out-voted and the loss may diverge; throughput is "
                                 "unaffected. Use --worker-fail 1 for a run the code provably tolerates.")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "breakdown": breakdown,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "breakdown": breakdown, "sanity": sanity,
             "samples_per_s": value * a.batch_size * a.num_workers,
         }
         def clean(o):                      # strict JSON: no NaN / Infinity literals
@@ -219,7 +261,6 @@ def main() -> int:
                 return [clean(v) for v in o]
             return o
         print(json.dumps(clean(out)), flush=True)
-    trainer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

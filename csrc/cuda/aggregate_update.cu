@@ -1,8 +1,9 @@
-// K7 + K8 + K9 (+ the second half of K3 / K4 / K6): fused "aggregate -> SGD-momentum -> parameter broadcast".
+// K7 + K8 + K9 (+ the second half of K3 / K4 / K6): fused "aggregate -> optimizer (SGD-momentum | Adam | AMSGrad) -> parameter broadcast".
 //
 // Reference: the PS first builds the aggregated gradient per tensor (mean: baseline_master.py:267-269; vote
-// winners / #groups: rep_master.py:166-168; Krum winner: baseline_master.py:278-296; Fourier recombination
-// Re(v^T R)/n: cyclic_master.py:125-129,171-172), then SGDModified.step (optim/sgd_modified.py:53-88), then
+// winners summed per tensor: rep_master.py:154-168 -- here divided by #groups, a documented deviation; Krum winner: baseline_master.py:278-296; Fourier recombination
+// Re(v^T R)/n: cyclic_master.py:125-129,171-172), then SGDModified.step / AdamModified.step (optim/sgd_modified.py:53-88,
+// optim/adam_modified.py:32-92), then
 // one MPI.Bcast per tensor (baseline_master.py:180-186).  Here a single streaming kernel per step does all
 // three: it reads only the gradient rows that contribute, updates momentum + fp32 master parameters in
 // place, and stores the fresh parameters directly into every worker's parameter arena -- with one NVLS
@@ -22,7 +23,9 @@ struct UpdateArgs {
   TileView tv;
   // optimizer ---------------------------------------------------------------------------------
   float* params;                  // PS master fp32 [D]
-  float* momentum;                // [D]
+  float* momentum;                // [D] SGD momentum buffer / Adam first moment
+  float* exp_avg_sq;              // [D] Adam second moment (null for SGD)
+  float* max_exp_avg_sq;          // [D] AMSGrad running maximum (null otherwise)
   const HyperParams* hp;
   const unsigned long long* step_ptr;
   unsigned long long first_step;  // step index at which momentum buffers are created (torch semantics)
@@ -41,6 +44,13 @@ __global__ void __launch_bounds__(DRC_THREADS) aggregate_update_kernel(const __g
   const HyperParams hp = *a.hp;
   const unsigned long long step = *a.step_ptr;
   const bool first = (step == a.first_step);
+  // Adam: step count t = updates so far + 1; bias corrections folded into the step size like the reference
+  float adam_step_size = 0.f;
+  if (hp.optimizer != 0) {
+    const double t = (double)(step - a.first_step + 1);
+    const double bc1 = 1.0 - pow((double)hp.beta1, t), bc2 = 1.0 - pow((double)hp.beta2, t);
+    adam_step_size = (float)((double)hp.lr * sqrt(bc2) / bc1);
+  }
   const int tile_end = a.tile_end > 0 ? a.tile_end : a.tv.ntiles;
   for (int tile = a.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     const int tensor = a.tv.tile_tensor[tile];
@@ -77,16 +87,34 @@ __global__ void __launch_bounds__(DRC_THREADS) aggregate_update_kernel(const __g
     float4 p = *reinterpret_cast<const float4*>(a.params + idx);
     float4 m = *reinterpret_cast<const float4*>(a.momentum + idx);
     float* gp = &g.x; float* pp = &p.x; float* mp = &m.x;
+    if (hp.optimizer == 0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float d = gp[e];
-      if (hp.weight_decay != 0.f) d = fmaf(hp.weight_decay, pp[e], d);
-      if (hp.momentum != 0.f) {
-        float b = first ? d : fmaf(hp.momentum, mp[e], (1.f - hp.dampening) * d);
-        mp[e] = b;
-        d = hp.nesterov ? fmaf(hp.momentum, b, d) : b;
+      for (int e = 0; e < 4; ++e) {
+        float d = gp[e];
+        if (hp.weight_decay != 0.f) d = fmaf(hp.weight_decay, pp[e], d);
+        if (hp.momentum != 0.f) {
+          float b = first ? d : fmaf(hp.momentum, mp[e], (1.f - hp.dampening) * d);
+          mp[e] = b;
+          d = hp.nesterov ? fmaf(hp.momentum, b, d) : b;
+        }
+        pp[e] = fmaf(-hp.lr, d, pp[e]);
       }
-      pp[e] = fmaf(-hp.lr, d, pp[e]);
+    } else {
+      float4 v = *reinterpret_cast<const float4*>(a.exp_avg_sq + idx);
+      float4 vm = (hp.optimizer == 2) ? *reinterpret_cast<const float4*>(a.max_exp_avg_sq + idx) : v;
+      float* vp = &v.x; float* vmp = &vm.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float d = gp[e];
+        if (hp.weight_decay != 0.f) d = fmaf(hp.weight_decay, pp[e], d);
+        mp[e] = fmaf(hp.beta1, mp[e], (1.f - hp.beta1) * d);
+        vp[e] = fmaf(hp.beta2, vp[e], (1.f - hp.beta2) * d * d);
+        float vv = vp[e];
+        if (hp.optimizer == 2) { vmp[e] = fmaxf(vmp[e], vv); vv = vmp[e]; }
+        pp[e] = fmaf(-adam_step_size, mp[e] / (sqrtf(vv) + hp.eps), pp[e]);
+      }
+      *reinterpret_cast<float4*>(a.exp_avg_sq + idx) = v;
+      if (hp.optimizer == 2) *reinterpret_cast<float4*>(a.max_exp_avg_sq + idx) = vm;
     }
     *reinterpret_cast<float4*>(a.momentum + idx) = m;
     *reinterpret_cast<float4*>(a.params + idx) = p;

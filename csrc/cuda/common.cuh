@@ -25,6 +25,8 @@ struct TensorMeta {
 struct HyperParams {             // lives in device memory so a captured graph sees updates
   float lr, momentum, weight_decay, dampening;
   int nesterov;
+  int optimizer;                 // 0: SGD-momentum (optim/sgd_modified.py:53-88), 1: Adam, 2: AMSGrad (optim/adam_modified.py:32-92)
+  float beta1, beta2, eps;
   int pad[3];
 };
 

@@ -35,7 +35,8 @@ class TensorMeta(C.Structure):
 
 class HyperParams(C.Structure):
     _fields_ = [("lr", C.c_float), ("momentum", C.c_float), ("weight_decay", C.c_float), ("dampening", C.c_float),
-                ("nesterov", C.c_int), ("pad", C.c_int * 3)]
+                ("nesterov", C.c_int), ("optimizer", C.c_int), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("pad", C.c_int * 3)]
 
 
 class TileView(C.Structure):
@@ -72,7 +73,7 @@ class ResolveArgs(C.Structure):
 class UpdateArgs(C.Structure):
     _fields_ = [("mode", C.c_int), ("grad_in", ptr), ("slot_stride", i64), ("select", ptr), ("K", C.c_int),
                 ("scale", C.c_float), ("recomb", ptr), ("tv", TileView), ("params", ptr), ("momentum", ptr),
-                ("hp", ptr), ("step_ptr", ptr), ("first_step", u64), ("grad_out", ptr), ("mc_params", ptr),
+                ("exp_avg_sq", ptr), ("max_exp_avg_sq", ptr), ("hp", ptr), ("step_ptr", ptr), ("first_step", u64), ("grad_out", ptr), ("mc_params", ptr),
                 ("dst", ptr * MAX_DST), ("ndst", C.c_int), ("done_counter", ptr), ("flags", FlagList),
                 ("tile_begin", C.c_int), ("tile_end", C.c_int)]
 

@@ -13,7 +13,7 @@ from typing import Optional
 APPROACHES = ("baseline", "maj_vote", "cyclic")
 MODES = ("normal", "geometric_median", "krum", "maj_vote")
 ERR_MODES = ("rev_grad", "constant", "random", "omniscient", "none")
-TRANSPORTS = ("nvl", "nccl", "gloo")
+TRANSPORTS = ("nvl", "nccl", "nccl_flat", "gloo")
 
 
 @dataclass
@@ -50,7 +50,11 @@ class JobConfig:
     weight_decay: float = 0.0
     nesterov: bool = False
     dampening: float = 0.0
-    optimizer: str = "sgd"          # sgd | adam (adam only on the collective transports)
+    optimizer: str = "sgd"          # sgd | adam (reference: src/optim/{sgd,adam}_modified.py); every transport
+    amsgrad: bool = False
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-8
     data_root: str = "./data"
     synthetic_size: int = 8192
     augment: bool = False

@@ -132,9 +132,11 @@ def aggregate_update(layout: ArenaLayout, grad_in: Addr, slot_stride: int, *, pa
                      step_ptr: Addr, done_counter: Addr, K: int, scale: float, select: Addr = None,
                      recomb: Addr = None, first_step: int = 1, grad_out: Addr = None, mc_params: Addr = None,
                      dst: Sequence[Addr] = (), flags: Sequence[Addr] = (), grid: Optional[int] = None,
-                     tile_range: Optional[tuple] = None, weights: Addr = None) -> None:
-    """Fused aggregate (select-sum, cyclic recombination, or real per-tensor ``weights`` [T, K]) + SGD-momentum +
-    parameter broadcast + flags."""
+                     tile_range: Optional[tuple] = None, weights: Addr = None, exp_avg_sq: Addr = None,
+                     max_exp_avg_sq: Addr = None) -> None:
+    """Fused aggregate (select-sum, cyclic recombination, or real per-tensor ``weights`` [T, K]) + optimizer step (SGD-momentum, or
+    Adam / AMSGrad when the hyper-parameter block says so: ``momentum`` = first moment, ``exp_avg_sq`` / ``max_exp_avg_sq`` = second
+    moment / its running maximum) + parameter broadcast + flags."""
     a = N.UpdateArgs()
     a.mode = 1 if recomb is not None else (2 if weights is not None else 0)
     if weights is not None:
@@ -150,6 +152,8 @@ def aggregate_update(layout: ArenaLayout, grad_in: Addr, slot_stride: int, *, pa
     a.tv = layout.tile_view(dev)
     a.params = addr(params)
     a.momentum = addr(momentum)
+    a.exp_avg_sq = addr(exp_avg_sq)
+    a.max_exp_avg_sq = addr(max_exp_avg_sq)
     a.hp = addr(hp)
     a.step_ptr = addr(step_ptr)
     a.first_step = first_step

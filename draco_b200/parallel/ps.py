@@ -35,7 +35,9 @@ def select_rule(cfg: JobConfig) -> str:
 
 
 def hyperparams_tensor(cfg: JobConfig, device) -> torch.Tensor:
-    hp = N.HyperParams(cfg.lr, cfg.momentum, cfg.weight_decay, cfg.dampening, int(cfg.nesterov))
+    opt = {"sgd": 0, "adam": 2 if getattr(cfg, "amsgrad", False) else 1}[cfg.optimizer]
+    hp = N.HyperParams(cfg.lr, cfg.momentum, cfg.weight_decay, cfg.dampening, int(cfg.nesterov), opt,
+                       float(cfg.adam_beta1), float(cfg.adam_beta2), float(cfg.adam_eps))
     raw = np.frombuffer(bytes(hp), dtype=np.uint8).copy()
     return torch.from_numpy(raw).to(device)
 
@@ -51,7 +53,10 @@ class FusedPS:
         self.P = cfg.num_workers
         self.params = params                       # fp32 [D] master copy (inside the exported region)
         self.grad_in = grad_in                     # fp32 [P, D] or complex64-as-fp32 [P, 2D]
-        self.momentum = layout.new_arena(device)
+        self.momentum = layout.new_arena(device)             # SGD momentum buffer / Adam first moment
+        # Adam / AMSGrad state lives in arenas too (checkpointed with the momentum: utils/checkpoint.py)
+        self.exp_avg_sq = layout.new_arena(device) if cfg.optimizer == "adam" else None
+        self.max_exp_avg_sq = layout.new_arena(device) if (cfg.optimizer == "adam" and getattr(cfg, "amsgrad", False)) else None
         self.hp = hyperparams_tensor(cfg, device)
         self.counters = torch.zeros(16, dtype=torch.int32, device=device)
         T = layout.ntensors
@@ -93,7 +98,8 @@ class FusedPS:
         ``b`` is voted on, applied and broadcast as soon as every worker has pushed it, while the workers are still
         back-propagating / pushing the later buckets; only the last bucket is on the critical path."""
         K, L = self.K, self.layout
-        common = dict(params=self.params, momentum=self.momentum, hp=self.hp, step_ptr=step_ptr,
+        common = dict(params=self.params, momentum=self.momentum, exp_avg_sq=self.exp_avg_sq, max_exp_avg_sq=self.max_exp_avg_sq,
+                      hp=self.hp, step_ptr=step_ptr,
                       done_counter=self.counters[0:1], first_step=1, grad_out=grad_out, mc_params=mc_params, dst=dst)
         n = 0
         if buckets is not None and self.rule in ("mean", "vote"):

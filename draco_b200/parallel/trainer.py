@@ -67,6 +67,9 @@ class Trainer:
         if cfg.transport == "nvl" and self.device.type == "cuda":
             from .fused_engine import FusedEngine
             self.engine = FusedEngine(cfg, rank, world, self.device, dataset)
+        elif cfg.transport == "nccl_flat" and self.device.type == "cuda":
+            from .flat_engine import FlatNcclEngine
+            self.engine = FlatNcclEngine(cfg, rank, world, self.device, dataset)
         else:
             from .collective_engine import CollectiveEngine
             self.engine = CollectiveEngine(cfg, rank, world, self.device, dataset)

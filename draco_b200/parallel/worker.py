@@ -78,7 +78,7 @@ class WorkerCompute:
         # the push kernel reads them through a device table of pointers -- no zero-fill, no accumulate-into-arena pass,
         # no gather (62 small kernels + 2 memsets per ResNet-18 backward otherwise).  The collective transports keep the
         # arena mode (p.grad = view of a zeroed flat arena).
-        self.zero_copy = self.device.type == "cuda" and cfg.transport == "nvl" and cfg.zero_copy_grads
+        self.zero_copy = self.device.type == "cuda" and cfg.transport in ("nvl", "nccl_flat") and cfg.zero_copy_grads
         self.grads: List[Tuple[torch.Tensor, Optional[torch.Tensor]]] = \
             [] if self.zero_copy else [self.binder.new_grad_arenas() for _ in range(self.R)]
         T = self.layout.ntensors
