@@ -40,7 +40,7 @@ class JobConfig:
     adversarial: int = 1
     worker_fail: int = 2
     group_size: int = 5
-    compress_grad: str = "compress"
+    compress_grad: str = "compress"  # lossless DRC2 codec on the wire (reference default: blosc on every gradient message)
     checkpoint_step: int = 0
     # ---- additions --------------------------------------------------------------------------
     num_workers: int = 0            # logical workers P (0: world_size - 1, like `mpirun -n P+1`)
@@ -85,8 +85,19 @@ class JobConfig:
             raise ValueError("--compress-grad must be 'compress' or 'None'")
         if self.approach == "cyclic" and self.num_workers < 2 * self.worker_fail + 1:
             raise ValueError("cyclic code needs num_workers >= 2*worker_fail + 1")
+        if self.approach == "cyclic" and 2 * self.worker_fail + 1 > 8:
+            raise ValueError("cyclic code: redundancy 2*worker_fail + 1 is limited to 8 (DRC_MAX_R)")
+        if self.approach == "maj_vote" and self.num_workers >= self.group_size > 0:
+            # all remainder workers join the last group (codes/repetition.py): it can hold up to 2r-1 members, the vote kernel 8
+            largest = self.group_size + self.num_workers % self.group_size
+            if largest > 8:
+                raise ValueError(f"repetition code: the last group would have {largest} members (num_workers % group_size "
+                                 f"remainder joins it); the vote kernel handles at most 8 (DRC_MAX_R) -- pick a group size that "
+                                 f"divides num_workers more evenly")
         if self.no_cuda:
             self.transport = "gloo"
+        if self.compress and self.transport == "nccl_flat":
+            raise ValueError("--transport nccl_flat is the uncompressed library comparator: pass --compress-grad None")
         if self.transport == "gloo":
             self.dtype = "fp32"
             self.cuda_graphs = False
@@ -155,6 +166,7 @@ def add_fit_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
     a("--nesterov", action="store_true", default=False)
     a("--dampening", type=float, default=0.0)
     a("--optimizer", type=str, default="sgd", choices=("sgd", "adam"))
+    a("--amsgrad", action="store_true", default=False, help="AMSGrad variant of --optimizer adam (reference: adam_modified.py:16)")
     a("--data-root", type=str, default=d.data_root)
     a("--synthetic-size", type=int, default=d.synthetic_size)
     a("--augment", action="store_true", default=False)

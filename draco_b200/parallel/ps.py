@@ -90,6 +90,11 @@ class FusedPS:
             f = (torch.randn(layout.total, generator=g) + 1.0) * torch.from_numpy(layout.valid_mask()).float()
             self.f = f.to(device)
 
+    @property
+    def opt_state(self) -> Dict[str, Optional[torch.Tensor]]:
+        """Optimizer arenas beyond ``momentum`` (Adam second moment, AMSGrad maximum) for checkpoints."""
+        return {"exp_avg_sq": self.exp_avg_sq, "max_exp_avg_sq": self.max_exp_avg_sq}
+
     def enqueue_step(self, step_ptr: torch.Tensor, *, mc_params: Optional[int], dst: Sequence[int], flags: Sequence[int],
                      grad_out: Optional[torch.Tensor] = None, buckets=None, wait_bucket=None) -> int:
         """Decode + update + broadcast for the step in ``*step_ptr``.  Returns the number of kernels launched.
@@ -157,7 +162,8 @@ class TorchPS:
         views = [params[s.offset: s.offset + s.numel] for s in layout.specs]
         self._views = views
         if cfg.optimizer == "adam":
-            self.optimizer = AdamModified(views, lr=cfg.lr, weight_decay=cfg.weight_decay)
+            self.optimizer = AdamModified(views, lr=cfg.lr, betas=(cfg.adam_beta1, cfg.adam_beta2), eps=cfg.adam_eps,
+                                          weight_decay=cfg.weight_decay, amsgrad=cfg.amsgrad)
         else:
             self.optimizer = SGDModified(views, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay,
                                          dampening=cfg.dampening, nesterov=cfg.nesterov)
@@ -172,7 +178,9 @@ class TorchPS:
     def momentum(self) -> Optional[torch.Tensor]:
         """SGD momentum buffers gathered into a flat arena (a copy), or None when there is nothing to save yet."""
         from ..optim import SGDModified
-        if not isinstance(self.optimizer, SGDModified) or self.cfg.momentum == 0:
+        if not isinstance(self.optimizer, SGDModified):
+            return self._gather("exp_avg")                  # Adam: the first moment plays the momentum's role in checkpoints
+        if self.cfg.momentum == 0:
             return None
         arena, found = self.layout.new_arena(self.device), False
         for v, spec in zip(self._views, self.layout.specs):
@@ -183,8 +191,37 @@ class TorchPS:
         return arena if found else None
 
     def load_momentum(self, arena: torch.Tensor) -> None:
+        key = "momentum_buffer" if self.cfg.optimizer != "adam" else "exp_avg"
         for v, spec in zip(self._views, self.layout.specs):
-            self.optimizer.state[v]["momentum_buffer"] = arena[spec.offset: spec.offset + spec.numel].clone()
+            self.optimizer.state[v][key] = arena[spec.offset: spec.offset + spec.numel].clone()
+
+    def _gather(self, key: str) -> Optional[torch.Tensor]:
+        arena, found = self.layout.new_arena(self.device), False
+        for v, spec in zip(self._views, self.layout.specs):
+            buf = self.optimizer.state.get(v, {}).get(key)
+            if buf is not None:
+                arena[spec.offset: spec.offset + spec.numel].copy_(buf)
+                found = True
+        return arena if found else None
+
+    @property
+    def opt_state(self) -> Dict[str, Optional[torch.Tensor]]:
+        if self.cfg.optimizer != "adam":
+            return {}
+        return {"exp_avg_sq": self._gather("exp_avg_sq"), "max_exp_avg_sq": self._gather("max_exp_avg_sq")}
+
+    def load_opt_state(self, arenas: Dict[str, torch.Tensor], step: int) -> None:
+        """Adam: second moment (+ AMSGrad maximum) and the per-tensor step count (= updates applied so far)."""
+        if self.cfg.optimizer != "adam":
+            return
+        for v, spec in zip(self._views, self.layout.specs):
+            st = self.optimizer.state[v]
+            st["step"] = int(step)
+            st.setdefault("exp_avg", torch.zeros_like(v))
+            for key, arena in arenas.items():
+                if arena is not None:
+                    st[key] = arena[spec.offset: spec.offset + spec.numel].clone()
+            st.setdefault("exp_avg_sq", torch.zeros_like(v))
 
     # --- per-tensor rules -----------------------------------------------------------------------
     def _vote_tensor(self, rows: List[torch.Tensor]) -> int:

@@ -162,9 +162,10 @@ class Trainer:
             dist.broadcast_object_list(box, src=self.eval_rank)
             bufs = box[0]
         if self.is_ps:
-            mom = getattr(getattr(eng, "ps", None), "momentum", None)
+            ps = getattr(eng, "ps", None)
+            mom = getattr(ps, "momentum", None)
             save_checkpoint(checkpoint_path(self.cfg.train_dir, step), eng.layout, eng.master_params(), mom, step,
-                            self.cfg, bufs)
+                            self.cfg, bufs, opt_state=getattr(ps, "opt_state", None))
 
     def resume(self, step: int) -> None:
         blob = load_checkpoint(checkpoint_path(self.cfg.train_dir, step))
@@ -172,13 +173,18 @@ class Trainer:
         ps = getattr(eng, "ps", None)
         if self.is_ps and hasattr(ps, "load_momentum"):
             # library-op PS: the momentum lives in the optimizer's state, rebuild it from the checkpoint
-            arena = eng.layout.new_arena(eng.master_params().device) if blob.get("momentum") else None
-            restore_into(blob, eng.layout, eng.master_params(), arena)
+            dev = eng.master_params().device
+            arena = eng.layout.new_arena(dev) if blob.get("momentum") else None
+            extra = {k: eng.layout.new_arena(dev) for k, v in (blob.get("opt_state") or {}).items() if v}
+            restore_into(blob, eng.layout, eng.master_params(), arena, extra)
+            if hasattr(ps, "load_opt_state"):
+                ps.load_opt_state(extra, step)              # before load_momentum: creates the Adam state entries
             if arena is not None:
                 ps.load_momentum(arena)
         else:
             mom = getattr(ps, "momentum", None)
-            restore_into(blob, eng.layout, eng.master_params(), mom if self.is_ps else None)
+            restore_into(blob, eng.layout, eng.master_params(), mom if self.is_ps else None,
+                         getattr(ps, "opt_state", None) if self.is_ps else None)
         if blob.get("buffers") and eng.worker is not None:
             eng.worker.model.load_state_dict(blob["buffers"], strict=False)
         eng.step = step + 1

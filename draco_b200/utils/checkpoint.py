@@ -26,7 +26,10 @@ def checkpoint_path(train_dir: str, step: int) -> str:
 
 
 def save_checkpoint(path: str, layout: ArenaLayout, params: torch.Tensor, momentum: Optional[torch.Tensor], step: int,
-                    cfg: JobConfig, buffers: Optional[Dict[str, torch.Tensor]] = None) -> None:
+                    cfg: JobConfig, buffers: Optional[Dict[str, torch.Tensor]] = None,
+                    opt_state: Optional[Dict[str, torch.Tensor]] = None) -> None:
+    """``momentum``: SGD momentum buffer / Adam first moment arena; ``opt_state``: further optimizer arenas by name
+    (Adam: ``exp_avg_sq``, AMSGrad: ``max_exp_avg_sq``) -- all saved per parameter tensor."""
     d = os.path.dirname(path)
     if d:
         os.makedirs(d, exist_ok=True)
@@ -36,7 +39,9 @@ def save_checkpoint(path: str, layout: ArenaLayout, params: torch.Tensor, moment
     if momentum is not None:
         mom = {layout.specs[i].name: layout.view(momentum, i).detach().float().cpu().contiguous().clone()
                for i in range(layout.ntensors)}
-    blob = {"format": "draco_b200/1", "step": int(step), "state_dict": state, "momentum": mom,
+    extra = {name: {layout.specs[i].name: layout.view(arena, i).detach().float().cpu().contiguous().clone()
+                    for i in range(layout.ntensors)} for name, arena in (opt_state or {}).items() if arena is not None}
+    blob = {"format": "draco_b200/1", "step": int(step), "state_dict": state, "momentum": mom, "opt_state": extra,
             "buffers": {k: v.detach().cpu().clone() for k, v in (buffers or {}).items()}, "config": cfg.to_dict()}
     tmp = path + ".tmp"
     torch.save(blob, tmp)
@@ -50,12 +55,17 @@ def load_checkpoint(path: str) -> dict:
     return blob
 
 
-def restore_into(blob: dict, layout: ArenaLayout, params: torch.Tensor, momentum: Optional[torch.Tensor]) -> int:
+def restore_into(blob: dict, layout: ArenaLayout, params: torch.Tensor, momentum: Optional[torch.Tensor],
+                 opt_state: Optional[Dict[str, torch.Tensor]] = None) -> int:
     with torch.no_grad():
         for i, spec in enumerate(layout.specs):
             layout.view(params, i).copy_(blob["state_dict"][spec.name])
             if momentum is not None and blob.get("momentum"):
                 layout.view(momentum, i).copy_(blob["momentum"][spec.name])
+            for name, arena in (opt_state or {}).items():
+                saved = (blob.get("opt_state") or {}).get(name)
+                if arena is not None and saved:
+                    layout.view(arena, i).copy_(saved[spec.name])
     return int(blob["step"])
 
 

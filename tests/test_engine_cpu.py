@@ -133,6 +133,30 @@ def test_checkpoint_resume_and_evaluator(tmp_path):
     assert ev.evaluate(max_evals=2, timeout_s=1.0) == 2
 
 
+def test_adam_state_is_checkpointed_and_resumed_bit_for_bit(tmp_path):
+    """--optimizer adam (reference: src/optim/adam_modified.py): first / second moment and the step count survive a
+    checkpoint -- the reference saves no optimizer state at all (baseline_master.py:237-243)."""
+    d = str(tmp_path) + "/"
+    kw = dict(approach="baseline", mode="normal", worker_fail=0, err_mode="none", train_dir=d, optimizer="adam", amsgrad=True,
+              lr=1e-3, max_steps=6)
+    t = Trainer(_cfg(eval_freq=3, **kw), rank=0, world=1, device=torch.device("cpu"), quiet=True)
+    t.fit(6)
+    final = t.engine.master_params().clone()
+    from draco_b200.utils.checkpoint import load_checkpoint
+    blob = load_checkpoint(d + "model_step_3")
+    assert set(blob["opt_state"]) == {"exp_avg_sq", "max_exp_avg_sq"} and blob["momentum"] is not None
+    t2 = Trainer(_cfg(eval_freq=10 ** 6, checkpoint_step=3, **kw), rank=0, world=1, device=torch.device("cpu"), quiet=True)
+    for _ in range(3):
+        t2.train_step()
+    assert torch.equal(t2.engine.master_params(), final)
+
+
+def test_config_rejects_oversized_vote_groups():
+    with pytest.raises(ValueError, match="members"):
+        _cfg(approach="maj_vote", mode="maj_vote", group_size=5, num_workers=9, worker_fail=0, err_mode="none").resolve(1)
+    _cfg(approach="maj_vote", mode="maj_vote", group_size=3, num_workers=7, worker_fail=0, err_mode="none").resolve(1)
+
+
 def test_compressed_wire_roundtrip_single_proc():
     t, losses = _run(_cfg(approach="baseline", mode="normal", worker_fail=0, err_mode="none", compress_grad="compress"), 3)
     assert np.isfinite(losses).all()

@@ -44,7 +44,10 @@ def test_fused_matches_library_op_engine():
     for kw in (dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad"),
                dict(approach="baseline", mode="normal", worker_fail=0, err_mode="none"),
                dict(approach="baseline", mode="krum", worker_fail=2, err_mode="constant"),
-               dict(approach="cyclic", worker_fail=2, err_mode="constant")):
+               dict(approach="cyclic", worker_fail=2, err_mode="constant"),
+               dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", optimizer="adam", lr=1e-3),
+               dict(approach="baseline", mode="normal", worker_fail=0, err_mode="none", optimizer="adam", amsgrad=True, lr=1e-3,
+                    weight_decay=1e-4)):
         a, la = _run(_cfg(**kw), 4)
         b, lb = _run(_cfg(transport="nccl", **kw), 4)
         pa, pb = a.engine.master_params(), b.engine.master_params()
