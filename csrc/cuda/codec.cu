@@ -3,8 +3,10 @@
 //
 // Reference: every gradient tensor goes through `blosc.pack_array(..., cname='snappy')` on the worker and
 // `blosc.unpack_array` on the PS (src/compress_gradient.py:7-15).  On NVLink the codec can only lose time against a
-// 770 GB/s link (that is why the fused transport does not use it), but it is a capability of the reference, it is
-// useful on the NCCL/Gloo transports across nodes, and it keeps checkpoints small.
+// 770 GB/s link, but it is a capability of the reference (--compress-grad compress is its default), so every transport
+// honours the flag: on the fused transport the worker encodes into a local buffer, packs it, and stream_push_kernel below
+// stores only the packed bytes into the PS's staging slot over NVLink (the byte count is read from device memory, so the whole
+// path stays inside the captured graph); the PS unpacks straight into the worker's gradient slot ahead of the decode.
 //
 // Stream format "DRC2":
 //   header  : 'DRC2' u32 | itemsize_flags u32 | raw_bytes u64 | block_elems u32 (=4096) | nblocks u32          (24 B)
@@ -14,8 +16,7 @@
 //
 // One CTA per 4096-element block; the elements are staged once in shared memory, planes are analysed with a CTA-wide
 // min/max, and bit-packing works on groups of 8 elements (= `bits` whole bytes), so no two threads share an output byte.
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "common.cuh"
 
 namespace {
 
@@ -226,5 +227,35 @@ int drc_codec_unpack(const void* stream_bytes, const long long* block_off, long 
   k<<<nblocks, CB_THREADS, CB_ELEMS * itemsize, stream>>>((const uint8_t*)stream_bytes, block_off, elems, itemsize, rot, (uint8_t*)dst, error);
   return (int)cudaGetLastError();
 }
+
+// Push `*nbytes` bytes of a packed stream into a peer buffer (16-byte stores; both buffers are 16-byte aligned and padded) and raise
+// the step-stamped flag from the last CTA -- the compressed twin of push_encode's store path.
+struct StreamPushArgs {
+  const uint4* src;
+  uint4* dst;                          // peer pointer (PS staging slot of this worker)
+  const long long* nbytes;             // device scalar: packed size
+  long long* nbytes_out;               // optional peer word receiving the size (diagnostics / byte accounting)
+  const unsigned long long* step_ptr;
+  unsigned int* done_counter;
+  unsigned long long* flag;
+};
+
+__global__ void __launch_bounds__(DRC_THREADS) stream_push_kernel(const __grid_constant__ StreamPushArgs a) {
+  const long long n16 = (*a.nbytes + 15) >> 4;
+  for (long long i = (long long)blockIdx.x * DRC_THREADS + threadIdx.x; i < n16; i += (long long)gridDim.x * DRC_THREADS) {
+    const uint4 v = a.src[i];
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(a.dst + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.nbytes_out) *a.nbytes_out = *a.nbytes;
+  if (grid_last_cta(a.done_counter)) {
+    if (threadIdx.x == 0 && a.flag) st_release_sys(a.flag, *a.step_ptr);
+  }
+}
+
+int drc_stream_push(const StreamPushArgs* args, int grid, cudaStream_t stream) {
+  stream_push_kernel<<<grid, DRC_THREADS, 0, stream>>>(*args);
+  return (int)cudaGetLastError();
+}
+int drc_sizeof_StreamPushArgs() { return (int)sizeof(StreamPushArgs); }
 
 }  // extern "C"

@@ -78,6 +78,11 @@ class UpdateArgs(C.Structure):
                 ("tile_begin", C.c_int), ("tile_end", C.c_int)]
 
 
+class StreamPushArgs(C.Structure):
+    _fields_ = [("src", ptr), ("dst", ptr), ("nbytes", ptr), ("nbytes_out", ptr), ("step_ptr", ptr), ("done_counter", ptr),
+                ("flag", ptr)]
+
+
 class CastArgs(C.Structure):
     _fields_ = [("src", ptr), ("dst", ptr), ("tv", TileView)]
 

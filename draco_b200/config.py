@@ -96,6 +96,9 @@ class JobConfig:
                                  f"divides num_workers more evenly")
         if self.no_cuda:
             self.transport = "gloo"
+        if self.compress and self.transport == "nvl" and self.err_mode == "omniscient":
+            raise ValueError("--err-mode omniscient reads the honest slots in PS memory while they arrive; with --compress-grad "
+                             "compress they only exist after the PS unpacked them -- pass --compress-grad None")
         if self.compress and self.transport == "nccl_flat":
             raise ValueError("--transport nccl_flat is the uncompressed library comparator: pass --compress-grad None")
         if self.transport == "gloo":

@@ -172,6 +172,19 @@ def aggregate_update(layout: ArenaLayout, grad_in: Addr, slot_stride: int, *, pa
     N.check(N.cuda().drc_aggregate_update(C.byref(a), grid or max(1, min(ntiles, sm_count() * 8)), _stream()), "aggregate_update")
 
 
+def stream_push(src: Addr, dst: Addr, nbytes: Addr, nbytes_out: Addr = None, *, step_ptr: Addr, done_counter: Addr, flag: Addr = None,
+                grid: int = 16) -> None:
+    """Store ``*nbytes`` bytes (device scalar) of a packed stream into a peer buffer and raise the step-stamped flag
+    (compressed push of the fused transport, csrc/cuda/codec.cu)."""
+    a = N.StreamPushArgs(addr(src), addr(dst), addr(nbytes), addr(nbytes_out), addr(step_ptr), addr(done_counter), addr(flag))
+    lib = N.cuda()
+    if not getattr(lib, "_stream_push_ready", False):
+        lib.drc_stream_push.argtypes = [C.c_void_p, C.c_int, N.ptr]
+        lib.drc_stream_push.restype = C.c_int
+        lib._stream_push_ready = True
+    N.check(lib.drc_stream_push(C.byref(a), int(grid), _stream()), "stream_push")
+
+
 def cast_params(layout: ArenaLayout, src: Addr, dst: Addr) -> None:
     dev = torch.device("cuda", torch.cuda.current_device())
     a = N.CastArgs(addr(src), addr(dst), layout.tile_view(dev))

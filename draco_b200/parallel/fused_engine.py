@@ -72,7 +72,11 @@ class FusedEngine:
         self.checksum_log: List[dict] = []
         self.timer = PhaseTimer(True) if cfg.profile_phases else None
         self._eager_steps = 0
-        self.overlap_push = cfg.overlap_push and not self.cyclic
+        # --compress-grad compress (reference default, src/compress_gradient.py:7-15): the encoded gradient is packed on the
+        # worker GPU and only the packed bytes cross NVLink into a PS staging slot; the PS unpacks into the worker's gradient
+        # slot ahead of the decode.  Whole-arena push (no bucket overlap / PS pipelining in this mode).
+        self.compress = bool(cfg.compress)
+        self.overlap_push = cfg.overlap_push and not self.cyclic and not self.compress
         # PS pipelining: decode + apply + broadcast each gradient bucket as soon as all workers pushed it
         self.pipeline_ps = (self.overlap_push and cfg.pipeline_ps and select_rule(cfg) in ("mean", "vote")
                             and cfg.err_mode != "omniscient")
@@ -116,6 +120,19 @@ class FusedEngine:
         mapB = self.symm.share("grad_in", exporters=[0], importers=all_procs)
         self.ps_grad_base = mapB[0].ptr
         self.ps_flag_base = mapB[0].ptr + self.P * D * self.esize
+        self.codec = None
+        if self.compress:
+            from ..utils.codec import DeviceStreamCodec
+            self.codec = DeviceStreamCodec(D * self.esize // 4, device)
+            cap = self.codec.capacity
+            if self.is_ps:
+                regS = self.symm.alloc("grad_stage", self.P * cap + 8 * self.P)
+                self.stage = regS.tensor[: self.P * cap].view(self.P, cap)
+                self.stage_bytes = regS.tensor[self.P * cap: self.P * cap + 8 * self.P].view(torch.int64)
+            mapS = self.symm.share("grad_stage", exporters=[0], importers=all_procs)
+            self.ps_stage_base = mapS[0].ptr
+            self.enc_local = {w: torch.zeros(D * self.esize // 4, dtype=torch.float32, device=device) for w in self.local_workers}
+            self.stream_local = {w: torch.zeros(cap, dtype=torch.uint8, device=device) for w in self.local_workers}
         self.mc_params = None
         if want_mc:
             self.mc_params = self.symm.bind_multicast("params")
@@ -267,6 +284,10 @@ class FusedEngine:
             else:
                 flags = [base + i * MAX_BUCKETS * FLAG_STRIDE for i in range(self.P)]
                 K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_ps); n += 1
+                if self.compress:                               # packed streams -> the workers' gradient slots
+                    slots = self.grad_in.view(self.P, -1)
+                    for i in range(self.P):
+                        self.codec.unpack(self.stage[i], slots[i]); n += 1
                 n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
                                           dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
         if self.is_ps:
@@ -345,6 +366,17 @@ class FusedEngine:
             K.omniscient(self.ps_grad_base, L.total, honest, w - 1, cfg.attack_magnitude, L.total,
                          step_ptr=self.step_dev, done_counter=self.push_counters[w:w + 1], flag=self.grad_flag_ptr(w))
             n += 2
+        elif self.compress:
+            enc, stream = self.enc_local[w], self.stream_local[w]
+            K.push_encode(L, g32, g16, enc.data_ptr(), flag=None, **push_kw)                 # encode + adversary, locally
+            nbytes = self.codec.pack(enc, stream)                                            # DRC2 stream, size on the device
+            K.stream_push(stream, self.ps_stage_base + (w - 1) * self.codec.capacity, nbytes,
+                          self.ps_stage_base + self.P * self.codec.capacity + 8 * (w - 1), step_ptr=self.step_dev,
+                          done_counter=self.push_counters[w:w + 1], flag=self.grad_flag_ptr(w),
+                          grid=self.cfg.push_ctas if self.rank != 0 else 2 * K.sm_count())
+            n += 4
+            if self.debug_checksum:
+                self._dbg_loopback(w, g32, g16, push_kw)
         else:
             K.push_encode(L, g32, g16, self.slot_ptr(w), flag=self.grad_flag_ptr(w), **push_kw)
             n += 1

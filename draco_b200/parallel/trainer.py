@@ -33,7 +33,11 @@ def init_distributed(transport: str) -> tuple:
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        if transport == "gloo" or not torch.cuda.is_available():
+        oversubscribed = torch.cuda.is_available() and world > torch.cuda.device_count()
+        if transport == "gloo" or not torch.cuda.is_available() or oversubscribed or os.environ.get("DRACO_BOOTSTRAP") == "gloo":
+            # Gloo-only bootstrap: CPU jobs, and GPU jobs with more processes than GPUs (several ranks share a device: NCCL
+            # refuses duplicate devices, while the fused transport only needs object exchange + barriers from the process group
+            # -- peer memory between two processes on ONE GPU works through the same VMM fd export/import)
             dist.init_process_group("gloo", rank=rank, world_size=world)
         else:
             torch.cuda.set_device(local)

@@ -149,3 +149,49 @@ def decompress_tensor(stream, dtype, shape) -> "torch.Tensor":
     if int(err.item()):
         raise ValueError("corrupt codec stream")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sync-free device path (fused transport): fixed worst-case buffers, every size stays on the device -> capturable in a graph
+# ---------------------------------------------------------------------------------------------------------------------
+class DeviceStreamCodec:
+    """Packs / unpacks a flat fp32 buffer of ``nfloats`` elements without any host synchronisation.
+
+    ``pack(src, out)`` writes a DRC2 stream into ``out`` (uint8, ``capacity`` bytes) and returns the device scalar holding its
+    length; ``unpack(stream, dst)`` decodes a stream (its index is read on the device).  Header and block count are static."""
+
+    def __init__(self, nfloats: int, device):
+        import torch
+        self.lib = _cuda_lib()
+        self.device = device
+        self.raw = nfloats * 4
+        self.flags = 4 | 0x100                                   # 32-bit words, rotated (sign bit leaves the exponent byte)
+        self.nblocks = (nfloats + BLOCK_ELEMS - 1) // BLOCK_ELEMS
+        self.base = STREAM_HEADER + 4 * self.nblocks
+        # worst case: every plane RAW = 1 mode byte + n bytes per plane, 4 planes per block
+        self.capacity = ((self.base + self.raw + 4 * self.nblocks + 15) // 16 + 1) * 16
+        hdr = struct.pack("<IIQII", 0x32435244, self.flags, self.raw, BLOCK_ELEMS, self.nblocks)
+        self.header = torch.frombuffer(bytearray(hdr), dtype=torch.uint8).to(device)
+        self.meta = torch.empty(max(self.nblocks, 1) * 16, dtype=torch.int32, device=device)
+        self.sizes = torch.empty(max(self.nblocks, 1), dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def pack(self, src, out):
+        import torch
+        st = torch.cuda.current_stream().cuda_stream
+        N.check(self.lib.drc_codec_plan(src.data_ptr(), self.raw, self.flags, self.meta.data_ptr(), self.sizes.data_ptr(), st), "codec_plan")
+        csum = torch.cumsum(self.sizes.to(torch.int64), 0)
+        offs = torch.cat([csum.new_zeros(1), csum[:-1]]) + self.base
+        out[:STREAM_HEADER].copy_(self.header)
+        out[STREAM_HEADER:self.base].copy_(self.sizes.view(torch.uint8))
+        N.check(self.lib.drc_codec_pack(src.data_ptr(), self.raw, self.flags, self.meta.data_ptr(), offs.data_ptr(), out.data_ptr(), st),
+                "codec_pack")
+        return (csum[-1:] + self.base).contiguous()              # int64 [1] on the device: packed bytes
+
+    def unpack(self, stream, dst) -> None:
+        import torch
+        sizes = stream[STREAM_HEADER:self.base].view(torch.int32).to(torch.int64)
+        csum = torch.cumsum(sizes, 0)
+        offs = torch.cat([csum.new_zeros(1), csum[:-1]]) + self.base
+        N.check(self.lib.drc_codec_unpack(stream.data_ptr(), offs.data_ptr(), self.raw, self.flags, dst.data_ptr(), self.err.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "codec_unpack")
