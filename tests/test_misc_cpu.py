@@ -1,4 +1,5 @@
 """CPU tests: cluster tool, bucket planning, op fallbacks (Conv2d / FusedBatchNorm2d / Linear on CPU are plain ATen)."""
+import pytest
 import json
 import os
 
@@ -200,3 +201,118 @@ def test_replica_dropout_cpu_masks_are_keyed():
     D.clear_context()
     l1.eval()
     assert torch.equal(l1(x), x)
+
+
+class _StubEc2:
+    """In-memory stand-in for a boto3 EC2 client: spot requests are fulfilled on the second poll, instances pass their status
+    checks on the second poll -- enough to exercise the whole Ec2Fleet lifecycle without AWS."""
+
+    def __init__(self):
+        self.inst, self.reqs, self.polls, self.calls = {}, {}, {}, []
+
+    def _new(self, n, name=None):
+        ids = []
+        for _ in range(n):
+            iid = f"i-{len(self.inst):04d}"
+            self.inst[iid] = {"InstanceId": iid, "State": {"Name": "pending"}, "PrivateIpAddress": f"10.0.0.{len(self.inst) + 1}",
+                              "LaunchTime": len(self.inst), "Tags": [{"Key": "Name", "Value": name}] if name else []}
+            ids.append(iid)
+        return ids
+
+    def run_instances(self, MinCount, MaxCount, TagSpecifications, **spec):
+        self.calls.append(("run_instances", spec))
+        ids = self._new(MaxCount, TagSpecifications[0]["Tags"][0]["Value"])
+        return {"Instances": [{"InstanceId": i} for i in ids]}
+
+    def request_spot_instances(self, SpotPrice, InstanceCount, Type, LaunchSpecification):
+        self.calls.append(("request_spot_instances", SpotPrice, LaunchSpecification))
+        out = []
+        for _ in range(InstanceCount):
+            rid = f"sir-{len(self.reqs):04d}"
+            self.reqs[rid] = {"SpotInstanceRequestId": rid, "State": "open", "InstanceId": None}
+            out.append(dict(self.reqs[rid]))
+        return {"SpotInstanceRequests": out}
+
+    def describe_spot_instance_requests(self, SpotInstanceRequestIds=None, Filters=None):
+        ids = SpotInstanceRequestIds or list(self.reqs)
+        for rid in ids:
+            self.polls[rid] = self.polls.get(rid, 0) + 1
+            if SpotInstanceRequestIds and self.polls[rid] >= 2 and not self.reqs[rid]["InstanceId"]:
+                self.reqs[rid].update(State="active", InstanceId=self._new(1)[0])
+        return {"SpotInstanceRequests": [dict(self.reqs[r]) for r in ids]}
+
+    def create_tags(self, Resources, Tags):
+        for i in Resources:
+            self.inst[i]["Tags"] = Tags
+
+    def describe_instance_status(self, InstanceIds, IncludeAllInstances):
+        out = []
+        for i in InstanceIds:
+            self.polls[i] = self.polls.get(i, 0) + 1
+            if self.polls[i] >= 2:
+                self.inst[i]["State"] = {"Name": "running"}
+            ok = "ok" if self.polls[i] >= 2 else "initializing"
+            out.append({"InstanceId": i, "InstanceState": self.inst[i]["State"], "InstanceStatus": {"Status": ok}, "SystemStatus": {"Status": ok}})
+        return {"InstanceStatuses": out}
+
+    def describe_instances(self, Filters):
+        name = Filters[0]["Values"][0]
+        mine = [i for i in self.inst.values() if any(t["Value"] == name for t in i.get("Tags", []))]
+        return {"Reservations": [{"Instances": mine}]}
+
+    def cancel_spot_instance_requests(self, SpotInstanceRequestIds):
+        for r in SpotInstanceRequestIds:
+            self.reqs[r]["State"] = "cancelled"
+
+    def terminate_instances(self, InstanceIds):
+        for i in InstanceIds:
+            self.inst[i]["State"] = {"Name": "terminated"}
+
+
+def test_ec2_fleet_lifecycle_spot_and_on_demand(tmp_path):
+    """launch (spot requests -> wait fulfilled -> tag -> wait running + status checks), summaries, live get_hosts (PS first),
+    idempotent re-launch, shutdown (cancel requests + terminate), on-demand launch, and the failure paths (reference:
+    tools/pytorch_ec2.py:128-257, 656-819)."""
+    from draco_b200.cli import cluster
+    cfg = cluster.Cfg(dict(cluster.DEFAULT_CFG, name="job7", n_instances=3, spot_price="12.5", image_id="ami-1", key_name="k",
+                           security_group=["sg-1"], poll_s=0.0, launch_timeout_s=5))
+    stub = _StubEc2()
+    fleet = cluster.Ec2Fleet(cfg, client=stub)
+    ids = fleet.launch()
+    assert len(ids) == 3 and fleet.summarize() == {"running": ids}
+    kind, price, spec = stub.calls[0]
+    assert kind == "request_spot_instances" and price == "12.5" and spec["SecurityGroupIds"] == ["sg-1"] and spec["ImageId"] == "ami-1"
+    files = cluster.get_hosts(cfg, str(tmp_path), fleet)
+    assert cfg["nodes"] == ["10.0.0.1", "10.0.0.2", "10.0.0.3"] and files["hosts"].splitlines()[0] == "10.0.0.1\tnode0"
+    assert fleet.launch() == ids and len(stub.inst) == 3                       # idempotent: no second fleet
+    res = fleet.shutdown()
+    assert sorted(res["terminated"]) == ids and fleet.summarize() == {"terminated": ids} and len(res["cancelled_requests"]) == 3
+    od = cluster.Ec2Fleet(cluster.Cfg(dict(cfg, name="job8", spot_price="", n_instances=2)), client=stub)
+    assert len(od.launch()) == 2 and stub.calls[-1][0] == "run_instances"
+    # a request that fails terminally raises instead of polling forever; a fleet that never comes up times out
+    bad = _StubEc2()
+    bad.describe_spot_instance_requests = lambda **kw: {"SpotInstanceRequests": [
+        {"SpotInstanceRequestId": r, "State": "failed", "InstanceId": None, "Status": {"Code": "price-too-low"}} for r in kw["SpotInstanceRequestIds"]]}
+    with pytest.raises(RuntimeError, match="price-too-low"):
+        cluster.Ec2Fleet(cfg, client=bad).launch()
+    slow = _StubEc2()
+    slow.describe_instance_status = lambda **kw: {"InstanceStatuses": []}
+    with pytest.raises(TimeoutError):
+        cluster.Ec2Fleet(cluster.Cfg(dict(cfg, spot_price="", launch_timeout_s=0.05)), client=slow).launch()
+
+
+def test_cluster_parallel_fanout_and_single_job_default(tmp_path, monkeypatch):
+    from draco_b200.cli import cluster
+    cfg = cluster.Cfg(dict(cluster.DEFAULT_CFG, nodes=["127.0.0.1", "localhost"], state_file=str(tmp_path / "s.json"),
+                           remote_dir=str(tmp_path)))
+    out = cluster.run_parallel(cfg, "echo hello-$((1+1))")
+    assert set(out) == {"127.0.0.1", "localhost"} and all(r["rc"] == 0 and "hello-2" in r["stdout"] for r in out.values())
+    launched = []
+    monkeypatch.setattr(cluster, "run_on", lambda c, n, cmd, t=60: launched.append((n, cmd)) or __import__("subprocess").CompletedProcess([], 0, "123\n", ""))
+    assert list(cluster.run(cfg, ["--max-steps", "1"])) == ["127.0.0.1"]        # ONE job on the first node (ADVICE r1)
+    launched.clear()
+    pids = cluster.run(cfg, ["--max-steps", "1"], all_nodes=True)
+    assert list(pids) == ["127.0.0.1", "localhost"] and "job_node1.log" in launched[1][1] and "--nnodes=1" in launched[1][1]
+    launched.clear()
+    cluster.run(cfg, [], nnodes=2)
+    assert "--node-rank=1" in launched[1][1] and "--nnodes=2" in launched[1][1]
