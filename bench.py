@@ -155,7 +155,8 @@ def main() -> int:
         wall = time.perf_counter() - t0
         e2e_ms = reduce_max(max(s.elapsed_time(e), wall * 1e3 if world == 1 else 0.0))
         h2d = reduce_sum(float(eng.worker.h2d_bytes if eng.local_workers else 0))
-        d2h = reduce_sum((12.0 if eng.local_workers else 0.0) + (4.0 if a.impl == "ours" else 0.0))   # loss/prec1/prec5 + watchdog word
+        # loss/prec1/prec5 + watchdog word + the step's device-side phase stamps (12 x int64)
+        d2h = reduce_sum((12.0 if eng.local_workers else 0.0) + (4.0 + 96.0 if a.impl == "ours" else 0.0))
         e2e = {"value": a.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "final_loss": mean_loss(last),
                "api": "Trainer.train_step_pipelined() + drain()",

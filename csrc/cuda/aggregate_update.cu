@@ -222,6 +222,20 @@ extern "C" int drc_step_add(unsigned long long* step, long long delta, cudaStrea
   return (int)cudaGetLastError();
 }
 
+// Phase stamp: ring[(step & 63) * 8 + col] = %globaltimer.  One thread; placed at phase boundaries of the captured step so that the
+// per-step Comp / Comm / Method / Update times the reference prints (src/worker/cyclic_worker.py:154-156, src/master/
+// cyclic_master.py:143) exist in graph mode too, measured on the device with no host synchronisation.
+__global__ void stamp_kernel(unsigned long long* ring, const unsigned long long* step_ptr, int col) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  ring[((*step_ptr) & 63ull) * 8ull + (unsigned long long)col] = t;
+}
+
+extern "C" int drc_stamp(unsigned long long* ring, const unsigned long long* step_ptr, int col, cudaStream_t stream) {
+  stamp_kernel<<<1, 1, 0, stream>>>(ring, step_ptr, col);
+  return (int)cudaGetLastError();
+}
+
 struct SetFlagArgs {
   FlagList flags;
   const unsigned long long* step_ptr;

@@ -170,6 +170,164 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                                          BLOCK_N, reinterpret_cast<float*>(sbuf));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the same layers: dW[co][tap][ci] = sum_px dy[px][co] * x[px + tap][ci], ALL NINE TAPS FROM ONE RESIDENT PATCH.
+//
+// The per-tap split-K kernel (conv_tap_tcgen05.cu) re-reads dy and a shifted x patch for every tap and wastes half of every MMA
+// (Cout = 64 rows of a 128-row instruction): 48 us against cuDNN's 29 us on the layer1 shape.  Here the roles are swapped and the
+// taps are stacked in M:
+//   D_g[m = (tap in pair, ci)][n = co]  +=  A_g[px][m] * B[px][n]        K = pixels of an 8 x 16 tile, 16 per MMA
+//   A_g : the x HALO patch (the very box the forward kernel loads) read MN-major: K rows = pixels; the two 64-channel M atoms of a
+//         tap pair are the SAME patch at two start offsets -- the descriptor's leading-dimension offset (LBO) is the byte distance
+//         between the taps, its stride between 8-pixel groups (SBO) the patch pitch of one image row (1280 B);
+//   B   : the dy tile [128 px][64 co], MN-major, dense.
+// Five accumulators (tap pairs (0,1) (2,3) (4,5) (6,7) (7,8); 320 TMEM columns) live across ALL tiles of the persistent CTA: one
+// 39 KB TMA stage and 40 full-rate MMAs per 128 pixels, no epilogue until the end.  Every CTA then writes one fp32 partial
+// [64][9][64] and wgrad_halo_reduce_kernel folds the per-CTA partials in a fixed order (bit-deterministic).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int WG_DY_BYTES = BLOCK_M * 128;                        // 16 KB: [128 px][64 co]
+constexpr int WG_STAGE = PATCH_STRIDE + WG_DY_BYTES;               // 39 KB
+constexpr int WG_STAGES = 4;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE + 1024 + 256;
+constexpr int WG_GROUPS = 5;
+constexpr int WG_TMEM_COLS = 512;
+
+struct HaloWgradArgs {
+  int N, H, W;
+  float* partial;                  // [grid][64 co][9 taps][64 ci]
+};
+
+__device__ __forceinline__ int wg_tap(int g, int half) { return g < 4 ? 2 * g + half : 7 + half; }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const HaloWgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* tmem_full = empty_bar + WG_STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wt = a.W / TW, ht = a.H / TH;
+  const int num_tiles = wt * ht * a.N;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_dy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<WG_TMEM_COLS>(tmem_base_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int w0 = (tile % wt) * TW, h0 = ((tile / wt) % ht) * TH, n0 = tile / (wt * ht);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sp = smem + stage * WG_STAGE;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(PATCH_BYTES + WG_DY_BYTES));
+        tma_load_4d(sp, &tmap_x, 0, w0 - 1, h0 - 1, n0, &full_bar[stage]);               // x halo patch (zero-filled outside)
+        tma_load_4d(sp + PATCH_STRIDE, &tmap_dy, 0, w0, h0, n0, &full_bar[stage]);       // dy tile
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, true, true);                   // both operands MN-major
+      int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t patch = smem_u32(smem + stage * WG_STAGE);
+        const uint32_t dyt = patch + PATCH_STRIDE;
+#pragma unroll 1
+        for (int ks = 0; ks < BLOCK_M / UMMA_K; ++ks) {                                  // 16 pixels = two image rows of the tile
+          const uint64_t db = make_desc(dyt + ks * (UMMA_K * 128), 1024, 1);
+#pragma unroll
+          for (int g = 0; g < WG_GROUPS; ++g) {
+            const int t0 = wg_tap(g, 0), t1 = wg_tap(g, 1);
+            const int o0 = (t0 / 3) * PW + (t0 % 3), o1 = (t1 / 3) * PW + (t1 % 3);     // patch pixel offsets of the two taps
+            const uint32_t a_addr = patch + (uint32_t)((2 * ks) * PW + o0) * 128u;
+            const uint64_t da = make_desc(a_addr, PW * 128, (uint32_t)((o1 - o0) * 128) >> 4);
+            umma_f16(tmem_base + g * BLOCK_N, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        tcgen05_commit(&empty_bar[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tcgen05_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (once): TMEM -> fp32 partial [co][tap][ci] =====================
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int m = q * 32 + lane;                                   // accumulator row = (tap in pair, ci)
+    const int half = m >> 6, ci = m & 63;
+    float* base = a.partial + (long long)blockIdx.x * (64 * 9 * 64) + ci;
+#pragma unroll 1
+    for (int g = 0; g < WG_GROUPS; ++g) {
+      const int tap = wg_tap(g, half);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BLOCK_N + c), v);
+        if (g == 4 && half == 0) continue;                         // tap 7 was already produced by group 3
+#pragma unroll
+        for (int j = 0; j < 32; ++j) base[((long long)(c + j) * 9 + tap) * 64] = __uint_as_float(v[j]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<WG_TMEM_COLS>(tmem_base);
+}
+
+// out[e] = sum over the per-CTA partials (8 interleaved subsets, each with up to 16 independent 16-byte loads in flight, combined
+// in a fixed order), written as bf16.  elems = 64 * 9 * 64; grid = elems / 4 / 32 CTAs of 256 threads.
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* partial, int parts, __nv_bfloat16* out) {
+  constexpr int ELEMS4 = 64 * 9 * 64 / 4;
+  __shared__ float4 s[8][32];
+  const int il = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  const int e4 = blockIdx.x * 32 + il;
+  const float4* p4 = reinterpret_cast<const float4*>(partial);
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int g0 = sub; g0 < parts; g0 += 8 * 16) {
+    float4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int g = g0 + 8 * u;
+      v[u] = g < parts ? __ldcg(p4 + (long long)g * ELEMS4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }
+  }
+  s[sub][il] = t;
+  __syncthreads();
+  if (sub == 0) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float4 v = s[k][il]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + (long long)e4 * 4) = o;
+  }
+}
+
 }  // namespace
 
 extern "C" int drc_conv_halo_supported(int H, int W, int Cin, int Cout) {
@@ -224,5 +382,41 @@ extern "C" int drc_conv_halo(const void* act, const void* wgt, void* out, int N,
     if (!cfg1) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); if (e != cudaSuccess) return (int)e; cfg1 = true; }
     kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tx, tw, tout, a);
   }
+  return (int)cudaGetLastError();
+}
+
+// dy: [N,H,W,64] bf16, x: [N,H,W,64] bf16 -> dw: [64,3,3,64] bf16 (arena layout); ws: drc_conv_halo_stat_slots(...) * 36864 floats.
+extern "C" int drc_conv_halo_wgrad(const void* dy, const void* x, void* dw, float* ws, int N, int H, int W, int num_sms, int device,
+                                   cudaStream_t stream) {
+  if (!drc_conv_halo_supported(H, W, 64, 64)) return -1;
+  if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -2;
+  CUtensorMap tx, tdy;
+  {
+    cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+    cuuint32_t box[4] = {64, (cuuint32_t)PW, PH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1000 + (int)r;
+  }
+  int r = encode_act(&tdy, dy, 64, W, H, N, TW, TH, 1, 1);
+  if (r) return 2000 + r;
+  HaloWgradArgs a;
+  a.N = N; a.H = H; a.W = W; a.partial = ws;
+  const int grid = drc_conv_halo_stat_slots(N, H, W, num_sms);
+  static bool cfgd = false;
+  if (!cfgd) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    cfgd = true;
+  }
+  wgrad_halo_tcgen05_kernel<<<grid, NUM_THREADS, WG_SMEM, stream>>>(tx, tdy, a);
+  int rc = (int)cudaGetLastError();
+  if (rc) return rc;
+  wgrad_halo_reduce_kernel<<<64 * 9 * 64 / 4 / 32, 256, 0, stream>>>(ws, grid, (__nv_bfloat16*)dw);
   return (int)cudaGetLastError();
 }

@@ -65,6 +65,8 @@ def _lib():
         lib.drc_conv_halo.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr] + [N.ptr] * 6
                                       + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
         lib.drc_conv_halo.restype = C.c_int
+        lib.drc_conv_halo_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 5 + [N.ptr]
+        lib.drc_conv_halo_wgrad.restype = C.c_int
         lib.drc_conv_stem_supported.argtypes = [C.c_int] * 4
         lib.drc_conv_stem_supported.restype = C.c_int
         lib.drc_conv_stem_wgrad_parts.argtypes = [C.c_int] * 4
@@ -210,6 +212,22 @@ def conv_stem_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return dw
 
 
+def conv3x3_halo_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Weight gradient [64, 64, 3, 3] (stored [Cout, 3, 3, Cin]) of the 64 -> 64 3x3 / stride-1 layers: all nine taps from one resident
+    halo patch per 128-pixel tile (csrc/cuda/conv_halo_tcgen05.cu: wgrad_halo_tcgen05_kernel)."""
+    from .. import _native as N
+    from . import kernels as K
+    lib = _lib()
+    n, _, h, w = x.shape
+    assert dy.is_contiguous(memory_format=torch.channels_last) and x.is_contiguous(memory_format=torch.channels_last)
+    sms = K.sm_count(dy.device)
+    ws = torch.empty(lib.drc_conv_halo_stat_slots(n, h, w, sms) * 64 * 9 * 64, dtype=torch.float32, device=dy.device)
+    dw = torch.empty((64, 3, 3, 64), dtype=torch.bfloat16, device=dy.device).permute(0, 3, 1, 2)
+    N.check(lib.drc_conv_halo_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, h, w, sms, dy.device.index,
+                                    torch.cuda.current_stream().cuda_stream), "conv_halo_wgrad")
+    return dw
+
+
 class _ConvStemFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, bn_req):
@@ -271,7 +289,10 @@ class _ConvGFn(torch.autograd.Function):
             else:
                 dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True)
         if ctx.needs_input_grad[1]:
-            dw = convg_wgrad_tcgen05(dy, x, weight.shape[2], ctx.stride)
+            if ctx.halo and os.environ.get("DRACO_WGRAD_HALO", "1") != "0":
+                dw = conv3x3_halo_wgrad(dy, x)
+            else:
+                dw = convg_wgrad_tcgen05(dy, x, weight.shape[2], ctx.stride)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum((0, 2, 3))
         return dx, dw, db, None, None

@@ -212,6 +212,16 @@ def set_flags(flags: Sequence[Addr], step_ptr: Addr, addend: int) -> None:
     N.check(N.cuda().drc_set_flags(C.byref(a), _stream()), "set_flags")
 
 
+def stamp(ring: Addr, step_ptr: Addr, col: int) -> None:
+    """ring[(step & 63)][col] = %globaltimer (ring: int64 [64, 8])."""
+    lib = N.cuda()
+    if not getattr(lib, "_stamp_ready", False):
+        lib.drc_stamp.argtypes = [N.ptr, N.ptr, C.c_int, N.ptr]
+        lib.drc_stamp.restype = C.c_int
+        lib._stamp_ready = True
+    N.check(lib.drc_stamp(addr(ring), addr(step_ptr), int(col), _stream()), "stamp")
+
+
 def step_add(step_ptr: Addr, delta: int = 1) -> None:
     N.check(N.cuda().drc_step_add(addr(step_ptr), delta, _stream()), "step_add")
 

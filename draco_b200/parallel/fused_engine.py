@@ -145,6 +145,11 @@ class FusedEngine:
         self.counters = torch.zeros(16, dtype=torch.int32, device=device)
         self.stamps_worker = torch.zeros(64, 2, dtype=torch.int64, device=device)   # %globaltimer trace of the spin waits
         self.stamps_ps = torch.zeros(64, 2, dtype=torch.int64, device=device)
+        # phase stamps [step & 63][col]: 0 worker compute done (push joined) | 1 PS decode done, update + broadcast about to start |
+        # 2 PS update + broadcast done.  Together with the wait stamps they give the reference's per-step Comp / Comm / Method /
+        # Update times in graph mode, on the device, with no host synchronisation (utils/metrics.py prints them every step).
+        self.stamps_phase = torch.zeros(64, 8, dtype=torch.int64, device=device)
+        self.default_phases = not cfg.profile_phases
         sched = generate_schedule(self.P, cfg.worker_fail, cfg.max_steps)
         self.schedule = sched
         use_adv = cfg.err_mode != "none" and cfg.worker_fail > 0
@@ -264,6 +269,8 @@ class FusedEngine:
                 for w in order:
                     n += self._enqueue_worker(w, step_host, self.push_stream)
         if self.local_workers:
+            if self.default_phases:
+                K.stamp(self.stamps_phase, self.step_dev, 0); n += 1
             comp_phase.__exit__(None, None, None)
             nvtx.range_pop()
         if self.is_ps:
@@ -280,7 +287,8 @@ class FusedEngine:
                     return 1
 
                 n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params, dst=[] if self.mc_params else self.dst_ptrs,
-                                          flags=self.param_flag_ptrs, buckets=self.worker.buckets, wait_bucket=wait_bucket)
+                                          flags=self.param_flag_ptrs, buckets=self.worker.buckets, wait_bucket=wait_bucket,
+                                          before_update=self._stamp_decode_done)
             else:
                 flags = [base + i * MAX_BUCKETS * FLAG_STRIDE for i in range(self.P)]
                 K.wait_flags(flags, self.step_dev, 0, self.error, cfg.spin_timeout_s, self.stamps_ps); n += 1
@@ -289,14 +297,46 @@ class FusedEngine:
                     for i in range(self.P):
                         self.codec.unpack(self.stage[i], slots[i]); n += 1
                 n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
-                                          dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs)
+                                          dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs,
+                                          before_update=self._stamp_decode_done)
         if self.is_ps:
+            if self.default_phases:
+                K.stamp(self.stamps_phase, self.step_dev, 2); n += 1
             nvtx.range_pop()
             ps_phase.__exit__(None, None, None)
             if self.debug_checksum:      # every gradient flag of this step has been waited for on this stream
                 self._dbg_ps_sums = self.grad_in.view(torch.int32).view(self.P, -1).sum(1, dtype=torch.int64)
         K.step_add(self.step_dev, 1); n += 1
         return n
+
+    def _stamp_decode_done(self) -> int:
+        if not self.default_phases:
+            return 0
+        K.stamp(self.stamps_phase, self.step_dev, 1)
+        return 1
+
+    def _phase_row(self, step: int) -> torch.Tensor:
+        """[12] int64 on the device: wait stamps (worker begin/end, PS begin/end) + the 8 phase stamps of ``step``."""
+        i = step & 63
+        return torch.cat([self.stamps_worker[i], self.stamps_ps[i], self.stamps_phase[i]])
+
+    def _phases_from_row(self, row) -> Dict[str, float]:
+        """Reference field names (seconds): t_fetch = waiting for parameters ("Comm"), t_comp_encode_push = forward/backward with the
+        fused encode + push ("Comp"; "Encode" is inside it), t_gather = PS waiting for the last gradient, t_decode = vote /
+        Fourier / Krum / median up to the start of the last update kernel ("Method"), t_update = fused optimizer + broadcast."""
+        ww0, ww1, pw0, pw1, comp_end, dec_end, upd_end = [int(v) for v in row[:7]]
+        out: Dict[str, float] = {}
+        if self.local_workers and ww1 >= ww0 > 0:
+            out["t_fetch"] = (ww1 - ww0) * 1e-9
+            if comp_end >= ww1:
+                out["t_comp_encode_push"] = (comp_end - ww1) * 1e-9
+        if self.is_ps and pw1 >= pw0 > 0:
+            out["t_gather"] = (pw1 - pw0) * 1e-9
+            if dec_end >= pw1:
+                out["t_decode"] = (dec_end - pw1) * 1e-9
+                if upd_end >= dec_end:
+                    out["t_update"] = (upd_end - dec_end) * 1e-9
+        return out
 
     def _enqueue_worker(self, w: int, step_host: Optional[int], push_stream) -> int:
         """Forward/backward + encode/push of logical worker ``w`` on the current stream (bucket pushes on ``push_stream``)."""
@@ -461,6 +501,7 @@ class FusedEngine:
         if not hasattr(self, "_mpin"):
             self._mpin = [(torch.zeros(3, dtype=torch.float32).pin_memory(), torch.zeros(1, dtype=torch.int32).pin_memory(),
                            torch.cuda.Event(blocking=True)) for _ in range(4)]
+            self._ppin = [torch.zeros(12, dtype=torch.int64).pin_memory() for _ in range(4)]
             self._mslot = 0
         slot = self._mslot
         self._mslot = (slot + 1) % len(self._mpin)
@@ -469,6 +510,8 @@ class FusedEngine:
             m = torch.stack([self.worker.metrics[w] for w in self.local_workers]).mean(0)
             pin_f.copy_(m, non_blocking=True)
         pin_e.copy_(self.error, non_blocking=True)
+        if self.default_phases:
+            self._ppin[slot].copy_(self._phase_row(self.step - 1), non_blocking=True)      # 96 B: the step's device-side timeline
         ev.record()
         return slot
 
@@ -479,10 +522,11 @@ class FusedEngine:
         wait_event(ev)
         if int(pin_e[0]):
             raise RuntimeError(f"rank {self.rank}: spin-wait watchdog fired (flag index {int(pin_e[0]) - 1}) -- a peer never arrived")
+        phases = self._phases_from_row(self._ppin[slot].tolist()) if self.default_phases else {}
         if not self.local_workers:
-            return {}
+            return phases
         v = pin_f.tolist()
-        return {"loss": v[0], "prec1": v[1], "prec5": v[2]}
+        return {"loss": v[0], "prec1": v[1], "prec5": v[2], **phases}
 
     def synchronize(self) -> None:
         torch.cuda.synchronize()

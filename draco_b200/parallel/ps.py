@@ -96,13 +96,14 @@ class FusedPS:
         return {"exp_avg_sq": self.exp_avg_sq, "max_exp_avg_sq": self.max_exp_avg_sq}
 
     def enqueue_step(self, step_ptr: torch.Tensor, *, mc_params: Optional[int], dst: Sequence[int], flags: Sequence[int],
-                     grad_out: Optional[torch.Tensor] = None, buckets=None, wait_bucket=None) -> int:
+                     grad_out: Optional[torch.Tensor] = None, buckets=None, wait_bucket=None, before_update=None) -> int:
         """Decode + update + broadcast for the step in ``*step_ptr``.  Returns the number of kernels launched.
 
         With ``buckets`` (the workers' push buckets, in arrival order) and ``wait_bucket(b)`` the PS is pipelined: bucket
         ``b`` is voted on, applied and broadcast as soon as every worker has pushed it, while the workers are still
         back-propagating / pushing the later buckets; only the last bucket is on the critical path."""
         K, L = self.K, self.layout
+        before_update = before_update or (lambda: 0)      # called right before the (last) fused update + broadcast kernel
         common = dict(params=self.params, momentum=self.momentum, exp_avg_sq=self.exp_avg_sq, max_exp_avg_sq=self.max_exp_avg_sq,
                       hp=self.hp, step_ptr=step_ptr,
                       done_counter=self.counters[0:1], first_step=1, grad_out=grad_out, mc_params=mc_params, dst=dst)
@@ -115,33 +116,43 @@ class FusedPS:
                     K.vote(L, self.grad_in, self.slot_stride, self.group_table, self.neq_mask, self.winner_slot,
                            self.winner_member, tile_range=(t0, t1), tensor_range=(min(idxs), max(idxs) + 1)); n += 2
                     G = self.group_table.shape[0]
+                    if bi == len(buckets) - 1:
+                        n += before_update()
                     K.aggregate_update(L, self.grad_in, self.slot_stride, K=G, scale=1.0 / G, select=self.winner_slot,
                                        tile_range=(t0, t1), flags=fl, **common); n += 1
                 else:
+                    if bi == len(buckets) - 1:
+                        n += before_update()
                     K.aggregate_update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0 / self.P,
                                        tile_range=(t0, t1), flags=fl, **common); n += 1
             return n
         common["flags"] = flags
+        _agg = K.aggregate_update
+
+        def _update(*a, **kw):                             # every rule below ends in exactly one fused update kernel
+            nonlocal n
+            n += before_update()
+            _agg(*a, **kw)
         if self.rule == "mean":
-            K.aggregate_update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0 / self.P, **common); n += 1
+            _update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0 / self.P, **common); n += 1
         elif self.rule == "vote":
             K.vote(L, self.grad_in, self.slot_stride, self.group_table, self.neq_mask, self.winner_slot, self.winner_member); n += 2
             G = self.group_table.shape[0]
-            K.aggregate_update(L, self.grad_in, self.slot_stride, K=G, scale=1.0 / G, select=self.winner_slot, **common); n += 1
+            _update(L, self.grad_in, self.slot_stride, K=G, scale=1.0 / G, select=self.winner_slot, **common); n += 1
         elif self.rule == "krum":
             K.krum_select(L, self.grad_in, self.slot_stride, self.P, self.cfg.worker_fail, self.pair_d2, self.select); n += 2
-            K.aggregate_update(L, self.grad_in, self.slot_stride, K=1, scale=1.0, select=self.select, **common); n += 1
+            _update(L, self.grad_in, self.slot_stride, K=1, scale=1.0, select=self.select, **common); n += 1
         elif self.rule == "geomedian" and self.gm is None:
             K.geometric_median_weights(L, self.grad_in, self.slot_stride, self.P, self.pair_d2, self.gm_weights); n += 2
-            K.aggregate_update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0, weights=self.gm_weights, **common); n += 1
+            _update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0, weights=self.gm_weights, **common); n += 1
         elif self.rule == "geomedian":
             iters = 48
             K.geometric_median(L, self.grad_in, self.slot_stride, self.P, self.gm, iters=iters); n += 2 * iters + 1
-            K.aggregate_update(L, self.gm.median, self.slot_stride, K=1, scale=1.0, **common); n += 1
+            _update(L, self.gm.median, self.slot_stride, K=1, scale=1.0, **common); n += 1
         elif self.rule == "cyclic":
             K.cyclic_project(L, self.grad_in, self.slot_stride, self.P, self.f, self.E); n += 1
             K.cyclic_locate(self.E, self.P, self.cfg.worker_fail, self.recomb, self.healthy, self.flagged); n += 1
-            K.aggregate_update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0 / self.P, recomb=self.recomb, **common); n += 1
+            _update(L, self.grad_in, self.slot_stride, K=self.P, scale=1.0 / self.P, recomb=self.recomb, **common); n += 1
         return n
 
 

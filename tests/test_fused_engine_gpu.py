@@ -272,6 +272,18 @@ def test_debug_checksum_verifies_every_pushed_gradient(kw):
         t.train_step()
 
 
+def test_phase_times_are_reported_every_step_in_graph_mode():
+    """The reference prints Comp / Comm / Encode / Method / Update every step (src/worker/cyclic_worker.py:154-156,
+    src/master/cyclic_master.py:143).  Here they come from %globaltimer stamps inside the captured step -- no --profile-phases, no
+    host synchronisation -- and ride on the pipelined metric read."""
+    t, _ = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", cuda_graphs=True), 5)
+    assert t.engine.graph is not None
+    m = t.train_step()
+    for k in ("t_fetch", "t_comp_encode_push", "t_gather", "t_decode", "t_update"):
+        assert k in m and 0 <= m[k] < 5.0, (k, m)
+    assert m["t_comp_encode_push"] > 0 and m["t_update"] > 0 and "loss" in m
+
+
 def test_profile_phases_on_the_fused_engine():
     t, _ = _run(_cfg(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", profile_phases=True), 1)
     m = t.train_step()

@@ -222,6 +222,12 @@ def test_conv3x3_halo_reuse_kernels(n, hw):
     dref = torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), padding=1)
     assert _rel_err(dx, dref) < 1.5e-2, _rel_err(dx, dref)
     assert torch.equal(conv3x3_halo(x, w, False, b), y)
+    # weight gradient: all nine taps from one resident halo patch (tap pairs stacked in M, MN-major views of the patch)
+    from draco_b200.ops.conv import conv3x3_halo_wgrad
+    dw = conv3x3_halo_wgrad(dy, x)
+    wref = torch.nn.grad.conv2d_weight(x.float(), (64, 64, 3, 3), dy.float(), padding=1)
+    assert dw.shape == wref.shape and _rel_err(dw, wref) < 1.5e-2, _rel_err(dw, wref)
+    assert torch.equal(conv3x3_halo_wgrad(dy, x), dw)
 
 
 @pytest.mark.timeout(300)

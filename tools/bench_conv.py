@@ -80,6 +80,8 @@ for (c, k, hw, ks, st) in shapes:
            "cudnn_wgrad_us": timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, *args, [False, True, False]))}
     if halo:
         row["tap_fprop_us"] = timeit(lambda: C.convg_tcgen05(x, w, (hw, hw), st))
+        row["tap_wgrad_us"] = row["wgrad_us"]
+        row["wgrad_us"] = timeit(lambda: C.conv3x3_halo_wgrad(dy, x))
     fl = 2.0 * N * (hw // st) ** 2 * k * c * ks * ks
     row["fprop_tflops"] = round(fl / row["fprop_us"] / 1e6, 1)
     rows.append(row)
