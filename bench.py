@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=("ours", "reference", "nccl", "nccl_flat"))
     ap.add_argument("--network", type=str, default="ResNet18")
+    ap.add_argument("--dataset", type=str, default="Cifar10", help="Cifar10 (3x32x32) | ImageNet (synthetic 3x224x224, 1000 classes: "
+                    "ResNets get the 7x7/s2 stem + max-pool, BASELINE.json config 5) | MNIST")
+    ap.add_argument("--synthetic-size", type=int, default=None)
     ap.add_argument("--approach", type=str, default="maj_vote")
     ap.add_argument("--mode", type=str, default="maj_vote")
     ap.add_argument("--batch-size", type=int, default=128)
@@ -87,11 +90,12 @@ def main() -> int:
     if world != a.gpus and rank == 0:
         print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     total_steps = 2 * (a.warmup + a.steps) + 8
-    cfg = JobConfig(network=a.network, dataset="Cifar10", approach=a.approach, mode=a.mode, batch_size=a.batch_size,
+    syn = a.synthetic_size or (8192 if a.dataset != "ImageNet" else max(512, 2 * a.batch_size * a.num_workers))
+    cfg = JobConfig(network=a.network, dataset=a.dataset, approach=a.approach, mode=a.mode, batch_size=a.batch_size,
                     num_workers=a.num_workers, group_size=a.group_size, worker_fail=a.worker_fail, err_mode=a.err_mode,
                     lr=0.01, momentum=0.9, max_steps=total_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
                     cuda_graphs=not a.no_cuda_graphs and a.impl in ("ours", "nccl_flat"), compress_grad="None", multicast=a.multicast,
-                    synthetic_size=8192, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas,
+                    synthetic_size=syn, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas,
                     pipeline_ps=not a.no_pipeline_ps,
                     **({"worker_streams": a.worker_streams} if a.worker_streams is not None else {}))
     trainer = Trainer(cfg, rank=rank, world=world, device=torch.device("cuda", local), quiet=True)
@@ -198,10 +202,10 @@ def main() -> int:
     if a.sanity_steps > 0 and a.impl == "ours" and a.approach == "maj_vote":
         losses = {}
         for fails in (1, 0) if os.environ.get("DRACO_BENCH_SANITY", "1") != "0" else ():
-            c2 = JobConfig(network=a.network, dataset="Cifar10", approach=a.approach, mode=a.mode, batch_size=a.batch_size,
+            c2 = JobConfig(network=a.network, dataset=a.dataset, approach=a.approach, mode=a.mode, batch_size=a.batch_size,
                            num_workers=a.num_workers, group_size=a.group_size, worker_fail=fails, err_mode=a.err_mode if fails else "none",
                            lr=0.01, momentum=0.9, max_steps=a.sanity_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
-                           cuda_graphs=not a.no_cuda_graphs, compress_grad="None", multicast=a.multicast, synthetic_size=8192,
+                           cuda_graphs=not a.no_cuda_graphs, compress_grad="None", multicast=a.multicast, synthetic_size=syn,
                            log_interval=10 ** 9, data_on_device=True,
                            **({"worker_streams": a.worker_streams} if a.worker_streams is not None else {}))
             t2 = Trainer(c2, rank=rank, world=world, device=dev, quiet=True)
@@ -223,7 +227,7 @@ def main() -> int:
     if rank == 0:
         value = a.steps / (ms / 1e3)
         base = None
-        headline = (a.network == "ResNet18" and a.approach == "maj_vote" and a.mode == "maj_vote" and a.group_size == 3
+        headline = (a.network == "ResNet18" and a.dataset == "Cifar10" and a.approach == "maj_vote" and a.mode == "maj_vote" and a.group_size == 3
                     and a.worker_fail == 3 and a.num_workers == 7 and a.batch_size == 128)
         try:
             if not headline:
@@ -241,7 +245,8 @@ def main() -> int:
             "impl": a.impl,
             "config": {"model": a.network + " (CIFAR variant, 11.17M params)" if a.network == "ResNet18" else a.network,
                        "global_batch": a.batch_size * a.num_workers, "per_worker_batch": a.batch_size,
-                       "seq_len": None, "image": "3x32x32", "parallelism": f"ps1+w{a.num_workers} on {world} gpu",
+                       "seq_len": None, "image": {"Cifar10": "3x32x32", "ImageNet": "3x224x224 (synthetic, 1000 classes)", "MNIST": "1x28x28"}.get(a.dataset),
+                       "dataset": a.dataset, "parallelism": f"ps1+w{a.num_workers} on {world} gpu",
                        "placement": eng.place.describe(), "code": f"repetition r={a.group_size} majority-vote" if a.approach == "maj_vote" else a.approach,
                        "adversaries_per_step": a.worker_fail, "err_mode": a.err_mode, "transport": transport,
                        "cuda_graphs": bool(cfg.cuda_graphs), "worker_streams": len(getattr(eng, "worker_streams", []) or []) or 1, "nvls_multicast": bool(getattr(eng, "mc_params", None)),

@@ -434,12 +434,17 @@ int launch_n(int block_n, const CUtensorMap& tx, const CUtensorMap& tw, const CU
                        : launch_g<128, B_MN, TMA_EPI>(tx, tw, tout, a, num_sms, stream);
 }
 
-bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-
-// patch shape for an iteration space of OH x OW pixels per image: BW * BH * BN == pixels
+// patch shape for an iteration space of OH x OW pixels per image: BW * BH * BN == pixels with BW | OW and BH | OH (the largest
+// power-of-two divisors that fit), so ANY image size tiles exactly -- 32 x 32 gives 32 x 4 x 1, 56 x 56 (ImageNet ResNets)
+// 8 x 8 x 2, 14 x 14 gives 2 x 2 x 32 and 7 x 7 one pixel of 128 images.
+int pow2_divisor(int v, int cap) {
+  int d = 1;
+  while (d * 2 <= cap && v % (d * 2) == 0) d *= 2;
+  return d;
+}
 void patch_shape(int OH, int OW, int pixels, int& BW, int& BH, int& BN) {
-  BW = OW < pixels ? OW : pixels;
-  BH = (pixels / BW) < OH ? (pixels / BW) : OH;
+  BW = pow2_divisor(OW, pixels);
+  BH = pow2_divisor(OH, pixels / BW);
   BN = pixels / (BW * BH);
 }
 
@@ -470,11 +475,10 @@ extern "C" int drc_convg_taps(int ks, int stride, int dgrad, int ph, int pw, int
 // 1 if the forward geometry x[N,H,W,Cin] -> y[N,H/stride,W/stride,Cout] (ks x ks filter, pad ks/2) is served.
 extern "C" int drc_convg_supported(int H, int W, int Cin, int Cout, int ks, int stride) {
   if (!(ks == 1 || ks == 3) || !(stride == 1 || stride == 2)) return 0;
-  if (!pow2(W) || !pow2(H) || H % stride || W % stride) return 0;
+  if (H % stride || W % stride) return 0;
   const int OH = H / stride, OW = W / stride;
-  if (OW > 64 || OW < 2 || OH < 2) return 0;
+  if (OW < 1 || OH < 1 || OW > 4096 || OH > 4096) return 0;
   if (Cin % 64 || Cout % 64) return 0;
-  if (OW * OH < 128 && 128 % (OW * OH)) return 0;
   return 1;
 }
 
@@ -600,11 +604,10 @@ extern "C" int drc_convg_wgrad_plan(int N, int H, int W, int Cin, int Cout, int 
 
 extern "C" int drc_convg_wgrad_supported(int H, int W, int Cin, int Cout, int ks, int stride) {
   if (!(ks == 1 || ks == 3) || !(stride == 1 || stride == 2)) return 0;
-  if (!pow2(W) || !pow2(H) || H % stride || W % stride) return 0;
+  if (H % stride || W % stride) return 0;
   const int OH = H / stride, OW = W / stride;
-  if (OW > 64 || OW < 2 || OH < 2) return 0;
+  if (OW < 1 || OH < 1 || OW > 4096 || OH > 4096) return 0;
   if (Cin % 64 || Cout % 64) return 0;
-  if (OW * OH < 64 && 64 % (OW * OH)) return 0;
   return 1;
 }
 

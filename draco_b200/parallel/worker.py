@@ -60,6 +60,9 @@ def make_model(cfg: JobConfig) -> torch.nn.Module:
     kwargs = {}
     if cfg.num_classes != 10 and (cfg.network.startswith("ResNet") or cfg.network.startswith("VGG")):
         kwargs["num_classes"] = cfg.num_classes
+    if cfg.dataset == "ImageNet" and cfg.network.startswith("ResNet"):
+        # BASELINE.json config 5: ImageNet-shaped ResNets (7x7 / stride-2 stem + max-pool, 224 x 224 inputs, 1000 classes)
+        kwargs.update(num_classes=1000, imagenet_stem=True)
     return build_model(cfg.network, **kwargs)
 
 

@@ -144,7 +144,10 @@ def _bn_ref(y):
 TAP_SHAPES = [(128, 64, 128, 32, 3, 2), (128, 128, 256, 16, 3, 2), (128, 256, 512, 8, 3, 2), (128, 64, 128, 32, 1, 2),
               (64, 128, 256, 16, 1, 2), (5, 256, 512, 8, 1, 2), (8, 64, 64, 32, 3, 1), (16, 128, 128, 16, 3, 1), (6, 64, 128, 16, 1, 1),
               (128, 128, 128, 16, 3, 1), (128, 256, 256, 8, 3, 1), (128, 512, 512, 4, 3, 1), (7, 512, 64, 2, 3, 1), (3, 128, 192, 4, 3, 1),
-              (32, 512, 512, 2, 3, 1)]
+              (32, 512, 512, 2, 3, 1),
+              # ImageNet-ResNet geometries: image sizes that are not powers of two tile exactly as well (8 x 8 x 2, 4 x 4 x 8, ...)
+              (6, 64, 64, 56, 3, 1), (6, 128, 128, 28, 3, 1), (9, 256, 256, 14, 3, 1), (20, 512, 512, 7, 3, 1), (6, 64, 128, 56, 3, 2),
+              (5, 256, 512, 14, 1, 2), (3, 64, 256, 56, 1, 1)]
 
 
 @pytest.mark.timeout(300)
