@@ -7,6 +7,7 @@ library is missing the call raises (see ``_native.cuda``).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Union
 
 import torch
@@ -317,10 +318,34 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: boo
     assert out.shape == (M, Nn) and out.stride(1) == 1
     bias_f32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
     bias_b16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
+    if (not a_mn and not b_mn and M >= 256 and Nn >= 128 and block_n in (0, 128, 256)
+            and os.environ.get("DRACO_GEMM_2CTA", "0") == "1"):
+        return gemm2_bf16(A, B, out=out, bias=bias, relu=relu, accumulate=accumulate, block_n=block_n)
     code = N.cuda().drc_gemm_bf16(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), out.data_ptr(),
                                   out.stride(0), int(out.dtype == torch.float32), M, Nn, K, bias_f32, bias_b16, int(relu),
                                   int(accumulate), block_n, sm_count(A.device), A.device.index, _stream())
     N.check(code, "gemm_bf16")
+    return out
+
+
+def gemm2_bf16(A: torch.Tensor, B: torch.Tensor, *, out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+               bias: Optional[torch.Tensor] = None, relu: bool = False, accumulate: bool = False, block_n: int = 0) -> torch.Tensor:
+    """``C[M, N] = A[M, K] B[N, K]^T`` on CTA PAIRS (tcgen05.mma.cta_group::2, 256 x block_n tiles, csrc/cuda/gemm2_tcgen05.cu)."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and A.dim() == 2 and B.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
+    M, Kd, Nn = A.shape[0], A.shape[1], B.shape[0]
+    if out is None:
+        out = torch.empty(M, Nn, dtype=out_dtype, device=A.device)
+    lib = N.cuda()
+    if not getattr(lib, "_gemm2_ready", False):
+        lib.drc_gemm2_bf16.argtypes = [N.ptr, N.i64, N.ptr, N.i64, N.ptr, N.i64] + [C.c_int] * 4 + [N.ptr, N.ptr] + [C.c_int] * 5 + [N.ptr]
+        lib.drc_gemm2_bf16.restype = C.c_int
+        lib._gemm2_ready = True
+    bias_f32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
+    bias_b16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
+    N.check(lib.drc_gemm2_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(), out.stride(0),
+                               int(out.dtype == torch.float32), M, Nn, Kd, bias_f32, bias_b16, int(relu), int(accumulate), block_n,
+                               sm_count(A.device), A.device.index, _stream()), "gemm2_bf16")
     return out
 
 

@@ -98,6 +98,28 @@ def test_linear_layer_forward_backward(batch, fin, fout):
     assert _rel_err(lin.bias.grad, b32.grad) < 2e-2
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("M,N,Kd,bn", [(256, 256, 64, 256), (512, 256, 512, 128), (1024, 768, 1024, 0), (4096, 512, 4608, 256),
+                                        (300, 264, 200, 128), (8192, 256, 2304, 0), (257, 130, 72, 0)])
+def test_gemm_cta_pair_kernel(K, M, N, Kd, bn):
+    """tcgen05.mma.cta_group::2: two CTAs of a cluster share one 256 x BLOCK_N MMA (csrc/cuda/gemm2_tcgen05.cu); ragged M / N / K,
+    bias + ReLU epilogue, fp32 output and accumulate mode, vs fp32 torch."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(M + N + Kd)
+    A = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
+    B = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    ref = A.float() @ B.float().t()
+    c = K.gemm2_bf16(A, B, block_n=bn)
+    assert _rel_err(c, ref) < 1e-2, _rel_err(c, ref)
+    c2 = K.gemm2_bf16(A, B, out_dtype=torch.float32, bias=bias, relu=True, block_n=bn)
+    assert _rel_err(c2, torch.relu(ref + bias)) < 1e-2
+    acc = torch.ones(M, N, device=dev, dtype=torch.float32)
+    K.gemm2_bf16(A, B, out=acc, accumulate=True, block_n=bn)
+    assert _rel_err(acc, ref + 1.0) < 1e-2
+    assert torch.equal(K.gemm2_bf16(A, B, block_n=bn), c)
+
+
 @pytest.mark.parametrize("n,cin,cout,hw", [(32, 64, 256, 16), (16, 256, 64, 8), (8, 512, 2048, 4), (128, 64, 64, 32)])
 def test_pointwise_conv_on_tcgen05(n, cin, cout, hw):
     from draco_b200.ops.conv import Conv2d, backend_counters
