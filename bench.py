@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--sanity-steps", type=int, default=12,
                     help="after the timed runs: train the same job for this many steps with ONE liar (which r=3 provably tolerates) "
                          "and with none, and report that the loss is finite and identical (0 = skip)")
+    ap.add_argument("--ps-stream", action="store_true", help="co-located PS on its own stream inside the captured graph")
     ap.add_argument("--worker-streams", type=int, default=None,
                     help="concurrent CUDA streams for logical workers sharing a GPU (default: the JobConfig default)")
     return ap.parse_args()
@@ -96,7 +97,7 @@ def main() -> int:
                     lr=0.01, momentum=0.9, max_steps=total_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
                     cuda_graphs=not a.no_cuda_graphs and a.impl in ("ours", "nccl_flat"), compress_grad="None", multicast=a.multicast,
                     synthetic_size=syn, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas,
-                    pipeline_ps=not a.no_pipeline_ps,
+                    pipeline_ps=not a.no_pipeline_ps, ps_stream=a.ps_stream,
                     **({"worker_streams": a.worker_streams} if a.worker_streams is not None else {}))
     trainer = Trainer(cfg, rank=rank, world=world, device=torch.device("cuda", local), quiet=True)
     eng = trainer.engine

@@ -64,6 +64,10 @@ class JobConfig:
     profile_phases: bool = False    # CUDA-event timers per phase (fetch/comp/encode/comm/decode/update); disables CUDA graphs
     multicast: str = "auto"         # auto | on | off  (NVLS multimem.st broadcast)
     spin_timeout_s: float = 60.0
+    ps_stream: bool = False         # PS co-located with workers consumes gradient buckets on its own stream (captured graph only).
+                                    # Off by default: its spin-wait kernels then depend on kernels of OTHER graph branches making
+                                    # progress, which holds only while every branch gets its own hardware queue
+                                    # (CUDA_DEVICE_MAX_CONNECTIONS >= number of concurrent streams)
     num_classes: int = 10
     deterministic: bool = True
     overlap_push: bool = True       # ship gradient buckets while the remaining layers are still back-propagating
@@ -177,6 +181,8 @@ def add_fit_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
     a("--metrics-file", type=str, default=None)
     a("--multicast", type=str, default="auto", choices=("auto", "on", "off"))
     a("--spin-timeout-s", type=float, default=d.spin_timeout_s)
+    a("--ps-stream", action="store_true", default=d.ps_stream,
+      help="co-located PS on its own stream inside the captured graph (set CUDA_DEVICE_MAX_CONNECTIONS=32)")
     a("--num-classes", type=int, default=10)
     a("--no-overlap-push", dest="overlap_push", action="store_false", default=True)
     return parser

@@ -230,6 +230,21 @@ class FusedEngine:
         cfg, L = self.cfg, self.layout
         n = 0
         nvtx = torch.cuda.nvtx
+        # PS co-located with workers (N = 1, 2, 4): inside the captured graph the PS part runs on ITS OWN stream, forked here, so it
+        # votes / applies / broadcasts every gradient bucket as soon as all P workers (local and remote) pushed it, while the local
+        # workers are still back-propagating -- instead of queueing behind them.  A bucket's parameters are
+        # rewritten only after EVERY worker's flag for it arrived, i.e. after every local worker is past those layers.  Eager steps
+        # keep the serial order (a first-time kernel load would synchronise with the spinning wait kernel).
+        ps_side = (self.is_ps and bool(self.local_workers) and self.pipeline_ps and step_host is None and cfg.ps_stream
+                   and torch.cuda.is_current_stream_capturing())
+        if ps_side:
+            if getattr(self, "_ps_stream", None) is None:
+                self._ps_stream = torch.cuda.Stream(device=self.device)
+            fork0 = torch.cuda.Event()
+            fork0.record(torch.cuda.current_stream())
+            self._ps_stream.wait_event(fork0)
+            with torch.cuda.stream(self._ps_stream):
+                n += self._enqueue_ps_part()
         if self.local_workers:
             wc = self.worker
             nvtx.range_push("draco/worker: fetch params + compute + encode/push")   # reference phases: Comm / Comp / Encode
@@ -273,7 +288,21 @@ class FusedEngine:
                 K.stamp(self.stamps_phase, self.step_dev, 0); n += 1
             comp_phase.__exit__(None, None, None)
             nvtx.range_pop()
-        if self.is_ps:
+        if ps_side:
+            torch.cuda.current_stream().wait_stream(self._ps_stream)
+        elif self.is_ps:
+            n += self._enqueue_ps_part()
+        if self.is_ps and self.debug_checksum:      # every gradient flag of this step has been waited for on this stream
+            self._dbg_ps_sums = self.grad_in.view(torch.int32).view(self.P, -1).sum(1, dtype=torch.int64)
+        K.step_add(self.step_dev, 1); n += 1
+        return n
+
+    def _enqueue_ps_part(self) -> int:
+        """Gather (wait for the gradient flags) + decode + optimizer + broadcast on the current stream."""
+        cfg = self.cfg
+        n = 0
+        nvtx = torch.cuda.nvtx
+        if True:
             ps_phase = self._phase("t_gather_decode_update_bcast")
             ps_phase.__enter__()
             nvtx.range_push("draco/ps: gather + decode + update + broadcast")            # reference: Method / Update time
@@ -299,14 +328,10 @@ class FusedEngine:
                 n += self.ps.enqueue_step(self.step_dev, mc_params=self.mc_params,
                                           dst=[] if self.mc_params else self.dst_ptrs, flags=self.param_flag_ptrs,
                                           before_update=self._stamp_decode_done)
-        if self.is_ps:
-            if self.default_phases:
-                K.stamp(self.stamps_phase, self.step_dev, 2); n += 1
-            nvtx.range_pop()
-            ps_phase.__exit__(None, None, None)
-            if self.debug_checksum:      # every gradient flag of this step has been waited for on this stream
-                self._dbg_ps_sums = self.grad_in.view(torch.int32).view(self.P, -1).sum(1, dtype=torch.int64)
-        K.step_add(self.step_dev, 1); n += 1
+        if self.default_phases:
+            K.stamp(self.stamps_phase, self.step_dev, 2); n += 1
+        nvtx.range_pop()
+        ps_phase.__exit__(None, None, None)
         return n
 
     def _stamp_decode_done(self) -> int:
