@@ -10,8 +10,10 @@ The B200 design keeps the capability (gradients become visible to the transport 
 while backward is still running, so the push overlaps backprop) but not the layering violation: a
 ``SplitBackwardMixin`` model exposes the same three drivers, implemented with autograd's
 post-accumulate-grad hooks; what happens to a finished gradient is a callback supplied by the worker
-runtime (``draco_b200.parallel.worker``), which typically enqueues the fused encode+push kernel for that
-bucket on a side stream.
+runtime.  ``parallel/worker.py::WorkerCompute.forward_backward`` drives every backward pass through them:
+``backward_normal(loss, on_ready)`` when the transport overlaps the push with backprop (the callback counts
+down the bucket and enqueues the fused encode+push kernel on a side stream), ``backward_coded`` for the
+earlier sub-batches of a cyclic-code worker, ``backward_single`` otherwise.
 """
 from __future__ import annotations
 

@@ -96,7 +96,8 @@ VGGSplit = make_split(VGG, "VGGSplit")
 
 def _factory(cfg: str, bn: bool, name: str):
     def make(num_classes: int = 10):
-        return VGG(make_layers(CFG[cfg], batch_norm=bn), num_classes=num_classes)
+        # every zoo model carries the layer-wise backward drivers the worker runtime uses (models/split.py)
+        return VGGSplit(make_layers(CFG[cfg], batch_norm=bn), num_classes=num_classes)
     make.__name__ = name
     return make
 

@@ -98,8 +98,15 @@ class WorkerCompute:
         self._param_bucket = {i: b for b, (_, _, idxs) in enumerate(self.buckets) for i in idxs}
         self._bucket_left: List[int] = []
         self._bucket_cb = None
-        for i, p in enumerate(self.binder.params):
-            p.register_post_accumulate_grad_hook(self._make_ready_hook(i))
+        # Gradient readiness comes from the MODEL's layer-wise backward driver (models/split.py: backward_normal fires
+        # on_ready(param_index, param) as each gradient becomes final, reverse layer order -- the reference's "send layer l while
+        # back-propagating layer l-1", resnet_split.py:431-623).  Models without the drivers get equivalent hooks here.
+        self._has_drivers = all(hasattr(self.model, d) for d in ("backward_normal", "backward_coded", "backward_single"))
+        if self._has_drivers:
+            assert [id(p) for p in self.model._split_params()] == [id(p) for p in self.binder.params]
+        else:
+            for i, p in enumerate(self.binder.params):
+                p.register_post_accumulate_grad_hook(self._make_ready_hook(i))
         self.model.train()
         self.has_dropout = any(isinstance(m, torch.nn.Dropout) for m in self.model.modules())
         c, h, w = self.model.input_shape if hasattr(self.model, "input_shape") else (3, 32, 32)
@@ -248,16 +255,18 @@ class WorkerCompute:
                                    n, c, h, w, torch.cuda.current_stream().cuda_stream), "prep_input")
         return out
 
+    def _on_grad_ready(self, i: int, _param=None) -> None:
+        """Parameter ``i``'s gradient is final: when it completes a bucket, hand the bucket to the transport."""
+        cb = self._bucket_cb
+        if cb is None:
+            return
+        b = self._param_bucket[i]
+        self._bucket_left[b] -= 1
+        if self._bucket_left[b] == 0:
+            cb(b)
+
     def _make_ready_hook(self, i: int):
-        def hook(_param):
-            cb = self._bucket_cb
-            if cb is None:
-                return
-            b = self._param_bucket[i]
-            self._bucket_left[b] -= 1
-            if self._bucket_left[b] == 0:
-                cb(b)
-        return hook
+        return lambda _param: self._on_grad_ready(i)
 
     def _dropout_step(self, step_host: Optional[int]):
         """Step source of the dropout key: the engine's device step counter when there is one (``self.step_dev``, set by the
@@ -305,10 +314,14 @@ class WorkerCompute:
                 self._bucket_left = [len(idxs) for _, _, idxs in self.buckets]
                 self._bucket_cb = on_bucket
             try:
-                if hasattr(self.model, "backward_single"):
-                    self.model.backward_single(loss)
+                if not self._has_drivers:
+                    loss.backward()                                      # permanent hooks (registered in __init__) report readiness
+                elif self._bucket_cb is not None:
+                    self.model.backward_normal(loss, on_ready=self._on_grad_ready)     # send-as-you-go: buckets leave during backward
+                elif self.R > 1 and k < self.R - 1:
+                    self.model.backward_coded(loss)                      # coded workers: collect, the encode happens after the last one
                 else:
-                    loss.backward()
+                    self.model.backward_single(loss)
             finally:
                 self._bucket_cb = None
                 if self.has_dropout:
