@@ -6,7 +6,8 @@
 // heavy part; everything else is O(n^3) per tensor.
 //
 // Device formulation: (a) `cyclic_project_kernel`: one streaming pass over the complex64 arena R[n][D]
-// producing E[T][n] with fp64 accumulation (segmented by tensor through the tile table);
+// producing per-tile partials with fp64 accumulation, folded per tensor in a fixed order by `cyclic_fold_kernel`
+// (E[T][n]; no atomics -> the decode is bit-reproducible);
 // (b) `cyclic_locate_kernel`: one thread per tensor runs the shared fp64 locator core
 // (csrc/common/locator_core.h) and emits v[T][n] as complex64; (c) the recombination Re(v^T R)/n is fused
 // with SGD + broadcast in aggregate_update.cu (mode 1).  No host round trip between (a), (b) and (c).
@@ -19,11 +20,14 @@ struct ProjectArgs {
   int n;
   const float* f;                 // [D] random projection factors (N(1,1), fixed at build time)
   TileView tv;
-  double* E;                      // [T][n][2] (re, im), must be zero on entry
+  double* E;                      // [T][n][2] (re, im): per-tensor totals, written by the fold kernel
+  double* Epart;                  // [ntiles][n][2] per-tile partials (workspace)
 };
 
+// Pass 1: every tile's contribution E_tile[i] = sum_d R_i[d] f[d] for all n workers at once (all loads of a tile issued up
+// front, ONE block reduction per tile) -> Epart.  No atomics: the summation order is fixed, so the decode is bit-reproducible.
 __global__ void __launch_bounds__(DRC_THREADS) cyclic_project_kernel(const __grid_constant__ ProjectArgs a) {
-  __shared__ double s_part[DRC_THREADS / 32][2];
+  __shared__ double s_part[DRC_THREADS / 32][2 * DRC_MAX_R];
   for (int tile = blockIdx.x; tile < a.tv.ntiles; tile += gridDim.x) {
     int tensor;
     const int valid = tile_valid(a.tv, tile, tensor);
@@ -31,40 +35,63 @@ __global__ void __launch_bounds__(DRC_THREADS) cyclic_project_kernel(const __gri
     const bool active = (int)threadIdx.x * 4 < valid;
     float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) f4 = *reinterpret_cast<const float4*>(a.f + idx);
-    for (int i = 0; i < a.n; ++i) {
-      double re = 0.0, im = 0.0;
-      if (active) {
-        const float4* src = reinterpret_cast<const float4*>(a.R + 2 * (i * a.slot_stride + idx));
-        float4 c0 = ld_f4(src), c1 = ld_f4(src + 1);
-        re = (double)c0.x * f4.x + (double)c0.z * f4.y + (double)c1.x * f4.z + (double)c1.z * f4.w;
-        im = (double)c0.y * f4.x + (double)c0.w * f4.y + (double)c1.y * f4.z + (double)c1.w * f4.w;
-      }
+    for (int i0 = 0; i0 < a.n; i0 += DRC_MAX_R) {             // workers in chunks of 8 (16 fp64 accumulators per thread)
+      double acc[2 * DRC_MAX_R];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        re += __shfl_xor_sync(0xffffffffu, re, o);
-        im += __shfl_xor_sync(0xffffffffu, im, o);
+      for (int ii = 0; ii < DRC_MAX_R; ++ii) {
+        const int i = i0 + ii;
+        double re = 0.0, im = 0.0;
+        if (i < a.n && active) {
+          const float4* src = reinterpret_cast<const float4*>(a.R + 2 * (i * a.slot_stride + idx));
+          float4 c0 = ld_f4(src), c1 = ld_f4(src + 1);
+          re = (double)c0.x * f4.x + (double)c0.z * f4.y + (double)c1.x * f4.z + (double)c1.z * f4.w;
+          im = (double)c0.y * f4.x + (double)c0.w * f4.y + (double)c1.y * f4.z + (double)c1.w * f4.w;
+        }
+        acc[2 * ii] = re; acc[2 * ii + 1] = im;
       }
-      if ((threadIdx.x & 31) == 0) { s_part[threadIdx.x >> 5][0] = re; s_part[threadIdx.x >> 5][1] = im; }
+      const int nj = 2 * (a.n - i0 < DRC_MAX_R ? a.n - i0 : DRC_MAX_R);
+#pragma unroll
+      for (int j = 0; j < 2 * DRC_MAX_R; ++j) {
+        if (j < nj) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+          if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][j] = acc[j];
+        }
+      }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        double sr = 0.0, si = 0.0;
+      if ((int)threadIdx.x < nj) {
+        double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < DRC_THREADS / 32; ++w) { sr += s_part[w][0]; si += s_part[w][1]; }
-        atomicAdd(&a.E[((long long)tensor * a.n + i) * 2 + 0], sr);
-        atomicAdd(&a.E[((long long)tensor * a.n + i) * 2 + 1], si);
+        for (int w = 0; w < DRC_THREADS / 32; ++w) t += s_part[w][threadIdx.x];
+        a.Epart[(long long)tile * 2 * a.n + 2 * i0 + threadIdx.x] = t;
       }
       __syncthreads();
     }
   }
 }
 
+// Pass 2: one warp per tensor folds its tiles' partials in a fixed order (lanes stride over the tiles, xor tree) -> E[T][n][2].
+__global__ void __launch_bounds__(32) cyclic_fold_kernel(const __grid_constant__ ProjectArgs a) {
+  const int t = blockIdx.x;
+  const TensorMeta m = a.tv.meta[t];
+  const long long tile0 = m.offset / DRC_TILE, ntile = (m.numel + DRC_TILE - 1) / DRC_TILE;
+  for (int j = 0; j < 2 * a.n; ++j) {
+    double s = 0.0;
+    for (long long q = threadIdx.x; q < ntile; q += 32) s += a.Epart[(tile0 + q) * 2 * a.n + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) a.E[(long long)t * 2 * a.n + j] = s;
+  }
+}
+
 extern "C" int drc_cyclic_project(const ProjectArgs* args, int grid, cudaStream_t stream) {
   cyclic_project_kernel<<<grid, DRC_THREADS, 0, stream>>>(*args);
+  cyclic_fold_kernel<<<args->tv.ntensors, 32, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }
 
 struct LocateArgs {
-  double* E;                      // [T][n][2]; zeroed after use so the next step can accumulate again
+  double* E;                      // [T][n][2]; zeroed after use (kept from the accumulate-in-place version; harmless)
   int T, n, s;
   double rel_tol;
   float2* recomb;                 // [T][n] out

@@ -97,7 +97,7 @@ class SetFlagArgs(C.Structure):
 
 
 class ProjectArgs(C.Structure):
-    _fields_ = [("R", ptr), ("slot_stride", i64), ("n", C.c_int), ("f", ptr), ("tv", TileView), ("E", ptr)]
+    _fields_ = [("R", ptr), ("slot_stride", i64), ("n", C.c_int), ("f", ptr), ("tv", TileView), ("E", ptr), ("Epart", ptr)]
 
 
 class LocateArgs(C.Structure):

@@ -228,9 +228,15 @@ def step_add(step_ptr: Addr, delta: int = 1) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ cyclic decode (K4)
+_epart_cache = {}
+
+
 def cyclic_project(layout: ArenaLayout, R: Addr, slot_stride: int, n: int, f: Addr, E: torch.Tensor) -> None:
-    """E[T, n, 2] (fp64, zero on entry) += R_i . f per tensor."""
-    a = N.ProjectArgs(addr(R), slot_stride, n, addr(f), layout.tile_view(E.device), E.data_ptr())
+    """E[T, n, 2] (fp64) = R_i . f per tensor: per-tile partials, then a fixed-order fold per tensor (deterministic)."""
+    key = (E.device, layout.ntiles, n)
+    if key not in _epart_cache:
+        _epart_cache[key] = torch.empty(layout.ntiles, n, 2, dtype=torch.float64, device=E.device)
+    a = N.ProjectArgs(addr(R), slot_stride, n, addr(f), layout.tile_view(E.device), E.data_ptr(), _epart_cache[key].data_ptr())
     N.check(N.cuda().drc_cyclic_project(C.byref(a), stream_grid(layout), _stream()), "cyclic_project")
 
 
