@@ -131,6 +131,8 @@ class FusedEngine:
                 self.stage_bytes = regS.tensor[self.P * cap: self.P * cap + 8 * self.P].view(torch.int64)
             mapS = self.symm.share("grad_stage", exporters=[0], importers=all_procs)
             self.ps_stage_base = mapS[0].ptr
+            # one codec (plan / size scratch) per local worker: workers sharing this GPU pack concurrently on their own streams
+            self.codec_w = {w: DeviceStreamCodec(D * self.esize // 4, device) for w in self.local_workers}
             self.enc_local = {w: torch.zeros(D * self.esize // 4, dtype=torch.float32, device=device) for w in self.local_workers}
             self.stream_local = {w: torch.zeros(cap, dtype=torch.uint8, device=device) for w in self.local_workers}
         self.mc_params = None
@@ -434,7 +436,7 @@ class FusedEngine:
         elif self.compress:
             enc, stream = self.enc_local[w], self.stream_local[w]
             K.push_encode(L, g32, g16, enc.data_ptr(), flag=None, **push_kw)                 # encode + adversary, locally
-            nbytes = self.codec.pack(enc, stream)                                            # DRC2 stream, size on the device
+            nbytes = self.codec_w[w].pack(enc, stream)                                       # DRC2 stream, size on the device
             K.stream_push(stream, self.ps_stage_base + (w - 1) * self.codec.capacity, nbytes,
                           self.ps_stage_base + self.P * self.codec.capacity + 8 * (w - 1), step_ptr=self.step_dev,
                           done_counter=self.push_counters[w:w + 1], flag=self.grad_flag_ptr(w),
