@@ -250,7 +250,7 @@ def main() -> int:
                        "dataset": a.dataset, "parallelism": f"ps1+w{a.num_workers} on {world} gpu",
                        "placement": eng.place.describe(), "code": f"repetition r={a.group_size} majority-vote" if a.approach == "maj_vote" else a.approach,
                        "adversaries_per_step": a.worker_fail, "err_mode": a.err_mode, "transport": transport,
-                       "cuda_graphs": bool(cfg.cuda_graphs), "worker_streams": len(getattr(eng, "worker_streams", []) or []) or 1, "nvls_multicast": bool(getattr(eng, "mc_params", None)),
+                       "cuda_graphs": bool(cfg.cuda_graphs), "worker_streams": len(getattr(eng, "worker_streams", None) or getattr(eng, "streams", None) or []) or 1, "nvls_multicast": bool(getattr(eng, "mc_params", None)),
                        "l2": "per-step working set (7x44.7 MB gradient slab + activations) exceeds the 126 MB L2; no explicit flush",
                        "images_per_s": value * a.batch_size * a.num_workers,
                        "note": ("adversaries are drawn over all workers each step like the reference (src/util.py:100-103), so "

@@ -8,7 +8,8 @@
 //
 // Protocol (one persistent pair per TPC, tiles strided over the pairs):
 //   * both CTAs: warp 0 = TMA producer for ITS operand slices; the loads of both CTAs complete on the LEADER's (rank 0) full barrier
-//     (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address in cluster shared memory), arrival count 2;
+//     (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address in cluster shared memory); the leader's
+//     arrive.expect_tx announces the bytes of both CTAs, the peer never arrives (no cross-CTA fence on the K loop);
 //   * leader only: warp 1 issues tcgen05.mma.cta_group::2; tcgen05.commit.cta_group::2 ... multicast::cluster releases the smem
 //     stage in BOTH CTAs (each producer waits on its own empty barrier) and publishes the accumulator to BOTH epilogues;
 //   * both CTAs: warps 4-7 drain their 128 TMEM lanes; all eight epilogue warps arrive on the leader's tmem_empty barrier
@@ -53,7 +54,9 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
   return out;
 }
 __device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default (.release.cta) semantics: the arrival orders nothing but the tcgen05 reads fenced before it; a cluster-scope release
+  // would cost a full memory barrier per call
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // this CTA's operand slice; completion is signalled on the barrier at `bar_cluster_addr` (the leader's)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar_cluster_addr) {
@@ -104,7 +107,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     prefetch_tmap(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     mbar_fence_init();
   }
@@ -130,8 +133,10 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const uint32_t lead_full = map_to_cta(&full_bar[stage], 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);     // both CTAs' bytes land on this barrier
-          else remote_arrive(lead_full);
+          // ONE arrival (the leader's) carrying the bytes of BOTH CTAs; the peer only issues its loads -- they complete on the
+          // leader's barrier (first measurement: a per-stage cluster-scope arrive from the peer = a memory barrier per K block,
+          // tensor pipe 38 % active, profiles/ncu_gemm2.md)
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
           const int k0 = kb * BLOCK_K;
           tma_load_2d_2sm(sa, &tmap_a, k0, m0, lead_full);
           tma_load_2d_2sm(sb, &tmap_b, k0, n0, lead_full);

@@ -7,8 +7,8 @@ All three products of a linear layer run on the same kernel without transpose co
     dx = dy W     A = dy (K-major)   B = W  (MN-major)
     dW = dy^T x   A = dy (MN-major)  B = x  (MN-major)
 
-Shapes whose rows are not 16-byte multiples (e.g. 10-wide logits as an MN-major operand) and non-bf16 / CPU tensors
-take the cuBLAS / ATen path -- that is a per-call shape gate, not a silent global fallback: ``backend_counters`` records
+Narrow heads (10 classes) are zero-padded to a multiple of 8 in the backward pass so that they stay on this kernel too; other
+shapes whose rows are not 16-byte multiples and non-bf16 / CPU tensors take the cuBLAS / ATen path -- that is a per-call shape gate, not a silent global fallback: ``backend_counters`` records
 which path served every call so tests and the bench can assert the tensor-core path ran.
 """
 from __future__ import annotations
@@ -47,6 +47,21 @@ class _LinearFn(torch.autograd.Function):
         dy2 = dy if dy.is_contiguous() else dy.contiguous()
         x2 = x
         dx = dw = db = None
+        nout = weight.shape[0]
+        if nout % 8 and weight.shape[1] >= 64 and x2.shape[1] >= 64 and K.gemm_supported(x2, weight):
+            # narrow heads (10 classes): a row of dy / a column block of W is not a 16-byte multiple, which TMA requires.  Pad the
+            # class dimension with zeros to the next multiple of 8 (two tiny copies) and stay on the tensor-core kernel.
+            pad = 8 - nout % 8
+            dy_p = F.pad(dy2, (0, pad))
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = dy2.sum(0)
+            if ctx.needs_input_grad[0]:
+                backend_counters["tcgen05"] += 1
+                dx = K.gemm_bf16(dy_p, F.pad(weight, (0, 0, 0, pad)), b_mn=True)
+            if ctx.needs_input_grad[1]:
+                backend_counters["tcgen05"] += 1
+                dw = K.gemm_bf16(dy_p, x2, a_mn=True, b_mn=True)[:nout]
+            return dx, dw, db
         if ctx.needs_input_grad[0]:
             if K.gemm_supported(dy2, weight) and weight.shape[1] >= 64:
                 backend_counters["tcgen05"] += 1

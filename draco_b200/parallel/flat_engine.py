@@ -88,6 +88,9 @@ class FlatNcclEngine:
                 seg[s.offset: s.offset + s.numel] = i
             self.seg = torch.from_numpy(seg).to(self.device)
             self.ntens = self.layout.ntensors
+            # last arena element of every tensor's tile range (padding between tensors is zero in every slot: it never mismatches)
+            nxt = [s.offset for s in self.layout.specs[1:]] + [D]
+            self.seg_end = torch.tensor([n - 1 for n in nxt], dtype=torch.int64, device=self.device)
 
     # ------------------------------------------------------------------ worker side (captured)
     def _encode(self, w: int) -> None:
@@ -131,8 +134,10 @@ class FlatNcclEngine:
     # ------------------------------------------------------------------ PS side
     def _tensor_equal(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         """[ntensors] bool: tensors of rows a and b are bit-equal (NaN never equal, +0 == -0: torch.equal semantics)."""
-        mism = (a != b).to(torch.float32)
-        cnt = torch.zeros(self.ntens, dtype=torch.float32, device=self.device).index_add_(0, self.seg, mism)
+        # segments are contiguous: mismatches per tensor = difference of an inclusive prefix sum at the segment ends
+        c = torch.cumsum((a != b).to(torch.int32), 0, dtype=torch.int64)
+        ends = c[self.seg_end]
+        cnt = ends - torch.cat([ends.new_zeros(1), ends[:-1]])
         return cnt == 0
 
     def _decode(self) -> torch.Tensor:

@@ -6,6 +6,8 @@ python -m draco_b200.build > gpurun_out/env.log 2>&1
 for s in "$@"; do
   case $s in
     recheck) timeout -k 10 600 python -m pytest tests/test_fused_engine_gpu.py -q -m gpu -p no:cacheprovider -k "compress or phase_times or two_processes or dropout or library_op" > gpurun_out/t_recheck.log 2>&1; echo "recheck rc=$?" ;;
+    gemmtests) timeout -k 10 600 python -m pytest tests/test_gemm_gpu.py -q -m gpu -p no:cacheprovider -k "gemm or linear" > gpurun_out/t_gemm.log 2>&1; echo "gemmtests rc=$?" ;;
+    gemmbench) timeout -k 10 600 python tools/bench_gemm.py --json gpurun_out/gemm_bench.json > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
     bench1) timeout -k 10 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench1.log 2>&1; echo "bench1 rc=$?" ;;
     bench1_flat) timeout -k 10 600 python bench.py --gpus 1 --steps 20 --warmup 5 --impl nccl_flat > gpurun_out/bench1_flat.log 2>&1; echo "bench1_flat rc=$?" ;;
     bench1_ps) CUDA_DEVICE_MAX_CONNECTIONS=32 timeout -k 10 600 python bench.py --gpus 1 --steps 20 --warmup 5 --ps-stream > gpurun_out/bench1_psstream.log 2>&1; echo "bench1_ps rc=$?" ;;
@@ -14,4 +16,4 @@ for s in "$@"; do
     launches) timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
   esac
 done
-tail -n 6 gpurun_out/t_recheck.log gpurun_out/bench1*.log 2>/dev/null | cut -c1-1500
+tail -n 6 gpurun_out/t_recheck.log gpurun_out/t_gemm.log gpurun_out/gemm_bench.log gpurun_out/bench1*.log 2>/dev/null | cut -c1-1500
