@@ -39,6 +39,19 @@ struct Gemm2Args {
   int accumulate;
 };
 
+// Tile rasterisation: tiles are walked in groups of GROUP_M row blocks x all column blocks, column-major inside a group, so the ~74
+// tiles in flight at any time cover ~8 x 9 blocks: (8 + 9) operand panels per wave instead of (2 + 32) -- the B panel set of an
+// 8192^3 problem no longer streams through L2 once per wave.
+constexpr int GROUP_M = 8;
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& mb, int& nb) {
+  const int per_group = GROUP_M * n_blocks;
+  const int g = tile / per_group, first = g * GROUP_M;
+  const int gm = (m_blocks - first) < GROUP_M ? (m_blocks - first) : GROUP_M;
+  const int r = tile - g * per_group;
+  mb = first + r % gm;
+  nb = r / gm;
+}
+
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -126,8 +139,10 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
-        const int m0 = (tile / n_blocks) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
-        const int n0 = (tile % n_blocks) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        int mb, nb;
+        tile_coords(tile, m_blocks, n_blocks, mb, nb);
+        const int m0 = mb * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+        const int n0 = nb * BLOCK_N + (int)rank * (BLOCK_N / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -178,7 +193,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     int acc = 0; uint32_t acc_phase = 0;
     const bool vec_ok = (args.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(args.C) & 15) == 0);
     for (int tile = pair; tile < num_tiles; tile += npairs) {
-      const int m0 = (tile / n_blocks) * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = (tile % n_blocks) * BLOCK_N;
+      int mb, nb;
+      tile_coords(tile, m_blocks, n_blocks, mb, nb);
+      const int m0 = mb * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = nb * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const int row = m0 + q * 32 + lane;

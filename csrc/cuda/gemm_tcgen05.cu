@@ -67,6 +67,18 @@ __device__ __forceinline__ uint32_t gemm_idesc() {
   return d;
 }
 
+// Tile rasterisation: groups of GROUP_M row blocks x all column blocks, column-major inside a group (the tiles in flight cover a
+// roughly square block of the output: fewer distinct operand panels per wave -> better L2 reuse on large problems).
+constexpr int GROUP_M = 8;
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& mb, int& nb) {
+  const int per_group = GROUP_M * n_blocks;
+  const int g = tile / per_group, first = g * GROUP_M;
+  const int gm = (m_blocks - first) < GROUP_M ? (m_blocks - first) : GROUP_M;
+  const int r = tile - g * per_group;
+  mb = first + r % gm;
+  nb = r / gm;
+}
+
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -115,7 +127,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blocks) * BLOCK_M, n0 = (tile % n_blocks) * BLOCK_N;
+        int mb_, nb_;
+        tile_coords(tile, m_blocks, n_blocks, mb_, nb_);
+        const int m0 = mb_ * BLOCK_M, n0 = nb_ * BLOCK_N;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -172,7 +186,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int acc = 0; uint32_t acc_phase = 0;
     const bool vec_ok = (args.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(args.C) & 15) == 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_blocks) * BLOCK_M, n0 = (tile % n_blocks) * BLOCK_N;
+      int mb_, nb_;
+        tile_coords(tile, m_blocks, n_blocks, mb_, nb_);
+        const int m0 = mb_ * BLOCK_M, n0 = nb_ * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const int row = m0 + q * 32 + lane;

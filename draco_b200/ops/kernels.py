@@ -308,8 +308,8 @@ def krum_select(layout: ArenaLayout, grad_in: Addr, slot_stride: int, P: int, s:
 # ------------------------------------------------------------------------------------------------ GEMM (K10)
 def gemm_bf16(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out: Optional[torch.Tensor] = None,
               out_dtype: torch.dtype = torch.bfloat16, bias: Optional[torch.Tensor] = None, relu: bool = False,
-              accumulate: bool = False, block_n: int = 0) -> torch.Tensor:
-    """``C[M, N] = op(A) op(B)^T`` on tcgen05 tensor cores.
+              accumulate: bool = False, block_n: int = 0, cta_pair: Optional[bool] = None) -> torch.Tensor:
+    """``C[M, N] = op(A) op(B)^T`` on tcgen05 tensor cores (``cta_pair``: force / forbid the cta_group::2 kernel; None = by size).
 
     K-major operands (default) are ``A[M, K]`` / ``B[N, K]``; with ``a_mn`` / ``b_mn`` the tensor passed is the
     transposed storage ``A[K, M]`` / ``B[K, N]`` (MN contiguous), so no transpose copy is ever needed.
@@ -324,8 +324,11 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: boo
     assert out.shape == (M, Nn) and out.stride(1) == 1
     bias_f32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
     bias_b16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
-    if (not a_mn and not b_mn and M >= 256 and Nn >= 128 and block_n in (0, 128, 256)
-            and os.environ.get("DRACO_GEMM_2CTA", "0") == "1"):
+    # large K-major problems go to the CTA-pair kernel (tcgen05.mma.cta_group::2): measured 1.04x cuBLAS at 4096^3, 0.95x at
+    # 16384 x 512 x 4608 vs 0.87x / 0.82x for the single-CTA kernel (profiles/gemm_bench_r2.json); small ones lose to it
+    pair = os.environ.get("DRACO_GEMM_2CTA", "auto") if cta_pair is None else ("1" if cta_pair else "0")
+    if (not a_mn and not b_mn and block_n in (0, 128, 256) and M >= 256 and Nn >= 128
+            and (pair == "1" or (pair == "auto" and M >= 2048 and Nn >= 512 and K >= 1024))):
         return gemm2_bf16(A, B, out=out, bias=bias, relu=relu, accumulate=accumulate, block_n=block_n)
     code = N.cuda().drc_gemm_bf16(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), out.data_ptr(),
                                   out.stride(0), int(out.dtype == torch.float32), M, Nn, K, bias_f32, bias_b16, int(relu),

@@ -42,8 +42,8 @@ def main():
         B = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
         out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
         t_ours = timeit(lambda: K.gemm_bf16(A, B, out=out), flush)
-        t_128 = timeit(lambda: K.gemm_bf16(A, B, out=out, block_n=128), flush) if N >= 128 else None
-        t_256 = timeit(lambda: K.gemm_bf16(A, B, out=out, block_n=256), flush) if N >= 256 else None
+        t_128 = timeit(lambda: K.gemm_bf16(A, B, out=out, block_n=128, cta_pair=False), flush) if N >= 128 else None
+        t_256 = timeit(lambda: K.gemm_bf16(A, B, out=out, block_n=256, cta_pair=False), flush) if N >= 256 else None
         t_2cta = None
         if M >= 256 and N >= 128 and os.environ.get("BENCH_2CTA", "1") == "1":
             try:
