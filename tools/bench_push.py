@@ -119,9 +119,10 @@ def main() -> int:
         row["push_frac_of_link"] = (max(row["push_gbs_per_gpu_egress"] if world > 1 else 0.0, row["ps_ingress_gbs"] or 0.0) / LINK_GBS) if world > 1 else None
         if world == 1:
             row["push_frac_of_hbm"] = 2 * P * nbytes / 1e6 / t_push / hbm          # local slot: read + write through HBM
+        G = len(groups.groups)
         if rank == 0:
             table = torch.from_numpy(groups.as_table()).to(dev)
-            G, T = table.shape[0], layout.ntensors
+            T = layout.ntensors
             neq = torch.zeros(G, T, dtype=torch.int32, device=dev)
             win = torch.zeros(G, T, dtype=torch.int32, device=dev)
             mom = layout.new_arena(dev)
