@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--sanity-steps", type=int, default=12,
                     help="after the timed runs: train the same job for this many steps with ONE liar (which r=3 provably tolerates) "
                          "and with none, and report that the loss is finite and identical (0 = skip)")
+    ap.add_argument("--wgrad-stream", type=str, default="auto", choices=("auto", "on", "off"),
+                    help="weight-gradient kernels on a side stream (auto: processes that host one worker)")
     ap.add_argument("--ps-stream", action="store_true", help="co-located PS on its own stream inside the captured graph")
     ap.add_argument("--worker-streams", type=int, default=None,
                     help="concurrent CUDA streams for logical workers sharing a GPU (default: the JobConfig default)")
@@ -97,7 +99,7 @@ def main() -> int:
                     lr=0.01, momentum=0.9, max_steps=total_steps + 4, eval_freq=10 ** 9, transport=transport, dtype="bf16",
                     cuda_graphs=not a.no_cuda_graphs and a.impl in ("ours", "nccl_flat"), compress_grad="None", multicast=a.multicast,
                     synthetic_size=syn, log_interval=10 ** 9, overlap_push=not a.no_overlap_push, push_ctas=a.push_ctas,
-                    pipeline_ps=not a.no_pipeline_ps, ps_stream=a.ps_stream,
+                    pipeline_ps=not a.no_pipeline_ps, ps_stream=a.ps_stream, wgrad_stream=a.wgrad_stream,
                     **({"worker_streams": a.worker_streams} if a.worker_streams is not None else {}))
     trainer = Trainer(cfg, rank=rank, world=world, device=torch.device("cuda", local), quiet=True)
     eng = trainer.engine
@@ -250,7 +252,7 @@ def main() -> int:
                        "dataset": a.dataset, "parallelism": f"ps1+w{a.num_workers} on {world} gpu",
                        "placement": eng.place.describe(), "code": f"repetition r={a.group_size} majority-vote" if a.approach == "maj_vote" else a.approach,
                        "adversaries_per_step": a.worker_fail, "err_mode": a.err_mode, "transport": transport,
-                       "cuda_graphs": bool(cfg.cuda_graphs), "worker_streams": len(getattr(eng, "worker_streams", None) or getattr(eng, "streams", None) or []) or 1, "nvls_multicast": bool(getattr(eng, "mc_params", None)),
+                       "cuda_graphs": bool(cfg.cuda_graphs), "wgrad_stream": a.wgrad_stream, "worker_streams": len(getattr(eng, "worker_streams", None) or getattr(eng, "streams", None) or []) or 1, "nvls_multicast": bool(getattr(eng, "mc_params", None)),
                        "l2": "per-step working set (7x44.7 MB gradient slab + activations) exceeds the 126 MB L2; no explicit flush",
                        "images_per_s": value * a.batch_size * a.num_workers,
                        "note": ("adversaries are drawn over all workers each step like the reference (src/util.py:100-103), so "

@@ -63,6 +63,7 @@ class JobConfig:
     debug_checksum: bool = False    # verify every pushed gradient: loopback re-encode vs what landed in the PS slot (eager mode)
     profile_phases: bool = False    # CUDA-event timers per phase (fetch/comp/encode/comm/decode/update); disables CUDA graphs
     multicast: str = "auto"         # auto | on | off  (NVLS multimem.st broadcast)
+    wgrad_stream: str = "auto"      # weight-gradient kernels on a side stream: auto (processes hosting ONE worker) | on | off
     spin_timeout_s: float = 60.0
     ps_stream: bool = False         # PS co-located with workers consumes gradient buckets on its own stream (captured graph only).
                                     # Off by default: its spin-wait kernels then depend on kernels of OTHER graph branches making
@@ -180,6 +181,7 @@ def add_fit_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
     a("--data-on-device", action="store_true", default=False)
     a("--metrics-file", type=str, default=None)
     a("--multicast", type=str, default="auto", choices=("auto", "on", "off"))
+    a("--wgrad-stream", type=str, default=d.wgrad_stream, choices=("auto", "on", "off"))
     a("--spin-timeout-s", type=float, default=d.spin_timeout_s)
     a("--ps-stream", action="store_true", default=d.ps_stream,
       help="co-located PS on its own stream inside the captured graph (set CUDA_DEVICE_MAX_CONNECTIONS=32)")

@@ -17,6 +17,31 @@ from torch import nn
 
 backend_counters = {"tcgen05": 0, "cudnn": 0}
 
+# Weight gradients on a SIDE STREAM: dW of a layer is needed only when its bucket is pushed, while dX feeds the rest of the backward
+# chain.  With this switch on, every wgrad kernel (+ its split-K fold) is enqueued on a side stream forked from the backward stream
+# after dy / x are ready; the chain (BatchNorm backward -> dgrad -> ...) continues on the backward stream and overlaps with it (the
+# BatchNorm kernels need no shared memory, so they co-reside with a convolution CTA on the same SM).  Consumers join explicitly:
+# ``join_wgrad_stream()`` makes the CURRENT stream (or ``waiter``) wait for every wgrad enqueued so far -- the transport calls it
+# before pushing a bucket, the worker after backward.  Set by the engine for processes that host ONE worker (a GPU that already
+# runs several workers concurrently has nothing to gain).  Same kernels, same order per tensor: bit-identical results.
+WGRAD_SIDE_STREAM = False
+_side_streams = {}
+
+
+def _wgrad_stream(device) -> "torch.cuda.Stream":
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def join_wgrad_stream(device, waiter: "torch.cuda.Stream" = None) -> None:
+    """``waiter`` (default: the current stream) waits for every weight-gradient kernel forked from the current stream so far."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    side = _side_streams.get(key)
+    if side is not None:
+        (waiter or torch.cuda.current_stream(device)).wait_stream(side)
+
 
 class _Conv1x1Fn(torch.autograd.Function):
     """x2: [M, Cin] (NHWC rows), w2: [Cout, Cin] -> y2: [M, Cout]."""
@@ -283,16 +308,23 @@ class _ConvGFn(torch.autograd.Function):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = dw = db = None
         backend_counters["tcgen05"] += 1
+        def wgrad():
+            if ctx.halo and os.environ.get("DRACO_WGRAD_HALO", "1") != "0":
+                return conv3x3_halo_wgrad(dy, x)
+            return convg_wgrad_tcgen05(dy, x, weight.shape[2], ctx.stride)
+
+        if ctx.needs_input_grad[1] and WGRAD_SIDE_STREAM:
+            side = _wgrad_stream(dy.device)
+            side.wait_stream(torch.cuda.current_stream(dy.device))          # dy and x are complete
+            with torch.cuda.stream(side):
+                dw = wgrad()
         if ctx.needs_input_grad[0]:
             if ctx.halo:
                 dx = conv3x3_halo(dy, weight, True)
             else:
                 dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True)
-        if ctx.needs_input_grad[1]:
-            if ctx.halo and os.environ.get("DRACO_WGRAD_HALO", "1") != "0":
-                dw = conv3x3_halo_wgrad(dy, x)
-            else:
-                dw = convg_wgrad_tcgen05(dy, x, weight.shape[2], ctx.stride)
+        if ctx.needs_input_grad[1] and dw is None:
+            dw = wgrad()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum((0, 2, 3))
         return dx, dw, db, None, None

@@ -34,6 +34,7 @@ import torch.distributed as dist
 from ..codes.adversary import attack_code, generate_schedule
 from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset
+from ..ops import conv as _conv_ops
 from ..ops import kernels as K
 from ..utils.metrics import PhaseTimer, limit_host_threads, wait_event
 from .arena import ArenaLayout
@@ -92,6 +93,10 @@ class FusedEngine:
                                         and not cfg.debug_checksum
                                         and max(len(self.place.local_workers(p)) for p in range(nprocs)) > 1)
         self._staged_step = -1
+        # one worker on this GPU (the 8-GPU topology): overlap the weight-gradient kernels with the rest of the backward chain
+        from ..ops import conv as _conv_ops_mod
+        _conv_ops_mod.WGRAD_SIDE_STREAM = (cfg.wgrad_stream == "on" or (cfg.wgrad_stream == "auto" and len(self.local_workers) == 1)) \
+            and not cfg.profile_phases
 
         if cfg.deterministic:
             torch.backends.cudnn.deterministic = True
@@ -390,6 +395,7 @@ class FusedEngine:
                     wc.upload_ptrs(_w, wc.R - 1, min(idxs), max(idxs) + 1)
                 ev = torch.cuda.Event()
                 ev.record()                                   # on the backward stream (autograd thread)
+                _conv_ops.join_wgrad_stream(self.device, push_stream)    # ... and the weight gradients of the side stream
                 with torch.cuda.stream(push_stream):
                     push_stream.wait_event(ev)
                     # few CTAs: the transfer is NVLink/ingress-bound and must not starve the backward kernels

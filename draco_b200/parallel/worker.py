@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from ..config import JobConfig
 from ..data import BatchPlan, TensorDataset, augment_cifar
 from ..models import build_model
+from ..ops import conv as _conv
 from ..ops import dropout as _dropout
 from ..ops import norm as _norm
 from ..ops.loss import accuracy, cross_entropy_with_metrics  # noqa: F401  (accuracy re-exported)
@@ -326,6 +327,8 @@ class WorkerCompute:
                 self._bucket_cb = None
                 if self.has_dropout:
                     _dropout.clear_context()
+            if self.device.type == "cuda":
+                _conv.join_wgrad_stream(self.device)         # weight gradients computed on the side stream (ops/conv.py) are final
             if self.zero_copy:
                 self.grad_ptrs(0, self.layout.ntensors)          # validate dtype / strides against the arena layout
                 self.grad_refs[wk][k] = [p.grad for p in self.binder.params]

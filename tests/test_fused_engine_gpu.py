@@ -320,6 +320,21 @@ def test_concurrent_worker_streams_are_bit_identical_to_serial(graphs):
             assert torch.equal(slots[honest[0] - 1], slots[w - 1])
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_wgrad_side_stream_is_bit_identical(graphs):
+    """--wgrad-stream: weight-gradient kernels forked onto a side stream overlap the rest of the backward chain; joins happen before a
+    bucket is pushed and after backward.  Same kernels per tensor => same bits, eager and under graph replay."""
+    from draco_b200.ops import conv as C
+    kw = dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", network="ResNet18",
+              dataset="Cifar10", batch_size=16, num_workers=3, dtype="bf16", synthetic_size=256, cuda_graphs=graphs, worker_streams=1)
+    a, la = _run(_cfg(wgrad_stream="off", **kw), 5)
+    assert not C.WGRAD_SIDE_STREAM
+    b, lb = _run(_cfg(wgrad_stream="on", **kw), 5)
+    assert C.WGRAD_SIDE_STREAM and C._side_streams
+    C.WGRAD_SIDE_STREAM = False
+    assert torch.equal(a.engine.master_params(), b.engine.master_params()) and la == lb
+
+
 def test_pipelined_metric_reads_return_the_same_numbers_one_step_late():
     kw = dict(approach="maj_vote", mode="maj_vote", group_size=3, worker_fail=1, err_mode="rev_grad", cuda_graphs=True)
     _, sync_losses = _run(_cfg(**kw), 6)
