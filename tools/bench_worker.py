@@ -16,8 +16,10 @@ torch.backends.cudnn.benchmark = False
 net = sys.argv[1] if len(sys.argv) > 1 else "ResNet18"
 out_dir = "gpurun_out"
 os.makedirs(out_dir, exist_ok=True)
-for mode in ("fused", "aten"):
-    os.environ["DRACO_BN"] = mode
+from draco_b200.ops import conv as _C  # noqa: E402
+for mode in ("fused", "fused_wgrad_stream", "aten"):
+    os.environ["DRACO_BN"] = "aten" if mode == "aten" else "fused"
+    _C.WGRAD_SIDE_STREAM = mode == "fused_wgrad_stream"
     cfg = JobConfig(network=net, dataset="Cifar10", approach="baseline", mode="normal", batch_size=128, num_workers=1,
                     dtype="bf16", synthetic_size=1024, transport="nvl").resolve(1)
     ds = synthetic_dataset("Cifar10", 1024)
