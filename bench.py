@@ -63,9 +63,40 @@ def parse():
     ap.add_argument("--wgrad-stream", type=str, default="auto", choices=("auto", "on", "off"),
                     help="weight-gradient kernels on a side stream (auto: processes that host one worker)")
     ap.add_argument("--ps-stream", action="store_true", help="co-located PS on its own stream inside the captured graph")
+    ap.add_argument("--timeline", type=str, default=None,
+                    help="after the timed runs, record 3 steps under torch.profiler and write <FILE>.rank<R>.txt: every kernel of "
+                         "this rank's GPU in start order (start us, duration us, stream, name) -- NOT a timed number")
     ap.add_argument("--worker-streams", type=int, default=None,
                     help="concurrent CUDA streams for logical workers sharing a GPU (default: the JobConfig default)")
     return ap.parse_args()
+
+
+def _write_timeline(path, trainer, rank, barrier):
+    """Kernel timeline of 3 consecutive steps on this rank's GPU (CUPTI through torch.profiler; graph replays included)."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            trainer.train_step_async()
+        torch.cuda.synchronize()
+    barrier()
+    raw = f"{path}.rank{rank}.trace.json"
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    prof.export_chrome_trace(raw)
+    evs = [e for e in json.load(open(raw)).get("traceEvents", []) if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    os.remove(raw)
+    evs.sort(key=lambda e: e["ts"])
+    if not evs:
+        return
+    t0 = evs[0]["ts"]
+    with open(f"{path}.rank{rank}.txt", "w") as fh:
+        fh.write("start_us dur_us gap_to_prev_end_us stream name\n")
+        last_end = t0
+        for e in evs:
+            st, en = e["ts"], e["ts"] + e.get("dur", 0)
+            fh.write(f"{st - t0:10.1f} {en - st:8.1f} {st - last_end:8.1f} {e.get('args', {}).get('stream', '?'):>4} {e['name'][:110]}\n")
+            last_end = max(last_end, en)
 
 
 def main() -> int:
@@ -196,6 +227,8 @@ def main() -> int:
                  "worker_wait_for_params_ms_mean": sum(ww) / len(ww) if ww else None,
                  "worker_wait_for_params_ms_min": min(ww) if ww else None} if traces and any(traces) else None
     m = eng.read_metrics()
+    if a.timeline:
+        _write_timeline(a.timeline, trainer, rank, barrier)
     trainer.close()
 
     # ------------------------------------------------------------------ sanity point: the code tolerates what it promises

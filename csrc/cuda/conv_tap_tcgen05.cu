@@ -6,8 +6,9 @@
 //   * strided fprop : the activation tensor map carries elementStrides {1, s, s, 1}, so ONE box load delivers the
 //                     BW x BH x BN *output* pixels' inputs for a tap (every s-th pixel, halo zero-filled);
 //   * strided dgrad : dx is split into its s x s parity classes; for class (ph, pw) only the taps with matching parity
-//                     contribute and they read dy with unit stride -- 1 + 2 + 2 + 4 = 9 taps over the four launches of a
-//                     3x3 / stride-2 layer (no zero-insertion, no wasted MMAs); the epilogue writes with pixel stride s;
+//                     contribute and they read dy with unit stride -- 4 + 2 + 2 + 1 = 9 taps over the four classes of a
+//                     3x3 / stride-2 layer (no zero-insertion, no wasted MMAs), all classes in ONE launch (class-major tile
+//                     list, longest first); the epilogue writes with pixel stride s;
 //   * strided wgrad : K-blocks are 64-pixel patches of dy; the matching x patch is a strided box shifted by the tap.
 //
 // A launch is described by a tap table (input offset + weight column per tap), so the stride-1 3x3 case is the
@@ -30,17 +31,23 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int NUM_THREADS = 256;
 constexpr int MAX_TAPS = 9;
+constexpr int MAX_CLASSES = 4;
 
 struct TapConvArgs {
   int N, OH, OW;               // iteration space: one GEMM row per (n, i, j), tiled in BW x BH x BN patches
   int Cred, Cn;                // reduction channels per tap / output channels
   int BW, BH, BN;
   int in_mul;                  // input coordinate = patch origin * in_mul + tap offset   (stride for fprop, 1 for dgrad)
-  int ntaps;
+  int ntaps;                   // taps of ALL classes
   int tap_dw[MAX_TAPS], tap_dh[MAX_TAPS];
   int tap_wcol[MAX_TAPS];      // column of the tap inside a weight row (tap index * Cin)
   int out_H, out_W;            // output tensor geometry
-  int out_mul, out_oh, out_ow; // output pixel = (i * out_mul + out_oh, j * out_mul + out_ow)
+  int out_mul;                 // output pixel = (i * out_mul + out_oh, j * out_mul + out_ow)
+  // Output classes: ONE launch covers every parity class of a strided dgrad.  Class c owns taps [cls_tap0[c], cls_tap0[c+1]) and
+  // writes the pixels (out_mul * i + cls_oh[c], out_mul * j + cls_ow[c]); tiles are numbered class-major, classes sorted by
+  // decreasing tap count (longest tiles first: the static round-robin over CTAs then balances).  Dense launches have one class.
+  int nclass;
+  int cls_tap0[MAX_CLASSES + 1], cls_oh[MAX_CLASSES], cls_ow[MAX_CLASSES];
   __nv_bfloat16* out;          // [N, out_H, out_W, Cn]
   const float* bias_f32;
   const __nv_bfloat16* bias_bf16;
@@ -77,9 +84,9 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const int wt = a.OW / a.BW, ht = a.OH / a.BH, nt = (a.N + a.BN - 1) / a.BN;
   const int m_tiles = wt * ht * nt;
   const int n_tiles = (a.Cn + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
+  const int class_tiles = m_tiles * n_tiles;
+  const int num_tiles = class_tiles * a.nclass;
   const int c_blocks = a.Cred / BLOCK_K;           // 64-channel slices per tap
-  const int k_blocks = a.ntaps * c_blocks;
   const bool want_stats = TMA_EPI && a.stat.partial != nullptr;
 
   if (warp == 0 && lane == 0) {
@@ -106,10 +113,12 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / n_tiles, n0 = (tile % n_tiles) * BLOCK_N;
+        const int cls = tile / class_tiles, ct = tile - cls * class_tiles;
+        const int mt = ct / n_tiles, n0 = (ct % n_tiles) * BLOCK_N;
         const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
+        const int tap0 = a.cls_tap0[cls], k_blocks = (a.cls_tap0[cls + 1] - tap0) * c_blocks;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          const int tap = kb / c_blocks, c0 = (kb - tap * c_blocks) * BLOCK_K;
+          const int tl = kb / c_blocks, c0 = (kb - tl * c_blocks) * BLOCK_K, tap = tap0 + tl;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
@@ -134,6 +143,8 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int cls = tile / class_tiles;
+        const int k_blocks = (a.cls_tap0[cls + 1] - a.cls_tap0[cls]) * c_blocks;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -167,7 +178,8 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const bool stat_keep = n_tiles == 1 || num_tiles <= (int)gridDim.x;
     int stat_col0 = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / n_tiles, n0 = (tile % n_tiles) * BLOCK_N;
+      const int cls = tile / class_tiles, ct = tile - cls * class_tiles;
+      const int mt = ct / n_tiles, n0 = (ct % n_tiles) * BLOCK_N;
       const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -191,7 +203,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int m = q * 32 + lane;                             // row of the tile = pixel of the patch (w fastest)
         const int pw = w0 + m % a.BW, ph = h0 + (m / a.BW) % a.BH, pn = nb0 + m / (a.BW * a.BH);
         const bool row_ok = pn < a.N;
-        __nv_bfloat16* orow = a.out + (((long long)pn * a.out_H + (ph * a.out_mul + a.out_oh)) * a.out_W + (pw * a.out_mul + a.out_ow)) * a.Cn;
+        __nv_bfloat16* orow = a.out + (((long long)pn * a.out_H + (ph * a.out_mul + a.cls_oh[cls])) * a.out_W + (pw * a.out_mul + a.cls_ow[cls])) * a.Cn;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
           uint32_t v[32];
@@ -421,7 +433,7 @@ int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& to
     configured = true;
   }
   const int m_tiles = (a.OW / a.BW) * (a.OH / a.BH) * ((a.N + a.BN - 1) / a.BN);
-  const int tiles = m_tiles * ((a.Cn + BLOCK_N - 1) / BLOCK_N);
+  const int tiles = m_tiles * ((a.Cn + BLOCK_N - 1) / BLOCK_N) * a.nclass;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, SMEM, stream>>>(tx, tw, tout, a);
   return (int)cudaGetLastError();
@@ -532,7 +544,8 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
     a.in_mul = stride;
     a.ntaps = drc_convg_taps(ks, stride, 0, 0, 0, a.tap_dh, a.tap_dw, tidx);
     for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
-    a.out_H = OH; a.out_W = OW; a.out_mul = 1; a.out_oh = a.out_ow = 0;
+    a.out_H = OH; a.out_W = OW; a.out_mul = 1;
+    a.nclass = 1; a.cls_tap0[0] = 0; a.cls_tap0[1] = a.ntaps; a.cls_oh[0] = a.cls_ow[0] = 0;
     if (tma_epi) {
       r = encode_act(&tout, out, Cout, OW, OH, N, a.BW, a.BH, a.BN, 1);
       if (r) return 3000 + r;
@@ -549,37 +562,36 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
     int tidx[MAX_TAPS];
     a.ntaps = drc_convg_taps(ks, 1, 1, 0, 0, a.tap_dh, a.tap_dw, tidx);
     for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
-    a.out_oh = a.out_ow = 0;
+    a.nclass = 1; a.cls_tap0[0] = 0; a.cls_tap0[1] = a.ntaps; a.cls_oh[0] = a.cls_ow[0] = 0;
     r = encode_act(&tout, out, Cin, W, H, N, a.BW, a.BH, a.BN, 1);
     if (r) return 3000 + r;
     return launch_n<true, true>(block_n, tx, tw, tout, a, num_sms, stream);
   }
-  bool zeroed = false;
-  if (ks == 1 && stride > 1) {                    // empty parity classes exist: zero dx before any class writes into it
+  // stride 2: the s x s parity classes of dx in ONE launch (class-major tile list, longest classes first)
+  struct Cls { int ph, pw, n, dh[MAX_TAPS], dw[MAX_TAPS], tidx[MAX_TAPS]; } cls[MAX_CLASSES];
+  int nc = 0, empty = 0;
+  for (int ph = 0; ph < stride; ++ph)
+    for (int pw = 0; pw < stride; ++pw) {
+      Cls c; c.ph = ph; c.pw = pw;
+      c.n = drc_convg_taps(ks, stride, 1, ph, pw, c.dh, c.dw, c.tidx);
+      if (c.n == 0) { ++empty; continue; }
+      int at = nc++;
+      while (at > 0 && cls[at - 1].n < c.n) { cls[at] = cls[at - 1]; --at; }
+      cls[at] = c;
+    }
+  if (empty) {                                    // classes that receive nothing (1x1 / stride 2) have to read as zero
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * H * W * Cin * 2, stream);
     if (e != cudaSuccess) return (int)e;
-    zeroed = true;
   }
-  for (int ph = 0; ph < stride; ++ph) {
-    for (int pw = 0; pw < stride; ++pw) {
-      int tidx[MAX_TAPS];
-      a.ntaps = drc_convg_taps(ks, stride, 1, ph, pw, a.tap_dh, a.tap_dw, tidx);
-      for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
-      if (a.ntaps == 0) {
-        // this parity class of dx receives nothing (1x1 / stride 2): it has to read as zero
-        if (!zeroed) {
-          cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * H * W * Cin * 2, stream);
-          if (e != cudaSuccess) return (int)e;
-          zeroed = true;
-        }
-        continue;
-      }
-      a.out_oh = ph; a.out_ow = pw;
-      int rc = launch_n<true, false>(block_n, tx, tw, tout, a, num_sms, stream);
-      if (rc) return rc;
+  a.nclass = nc; a.ntaps = 0;
+  for (int c = 0; c < nc; ++c) {
+    a.cls_tap0[c] = a.ntaps; a.cls_oh[c] = cls[c].ph; a.cls_ow[c] = cls[c].pw;
+    for (int t = 0; t < cls[c].n; ++t, ++a.ntaps) {
+      a.tap_dh[a.ntaps] = cls[c].dh[t]; a.tap_dw[a.ntaps] = cls[c].dw[t]; a.tap_wcol[a.ntaps] = cls[c].tidx[t] * Cin;
     }
   }
-  return 0;
+  a.cls_tap0[nc] = a.ntaps;
+  return launch_n<true, false>(block_n, tx, tw, tout, a, num_sms, stream);
 }
 
 namespace {

@@ -24,23 +24,32 @@ backend_counters = {"tcgen05": 0, "cudnn": 0}
 # ``join_wgrad_stream()`` makes the CURRENT stream (or ``waiter``) wait for every wgrad enqueued so far -- the transport calls it
 # before pushing a bucket, the worker after backward.  Set by the engine for processes that host ONE worker (a GPU that already
 # runs several workers concurrently has nothing to gain).  Same kernels, same order per tensor: bit-identical results.
+# Requires gradients that are STOLEN by autograd (p.grad is None before backward, the zero-copy mode of the worker): an
+# accumulation ``p.grad += dw`` would run on the backward stream without waiting for the side stream.
 WGRAD_SIDE_STREAM = False
 _side_streams = {}
+_side_pending = set()        # keys whose side stream holds work the backward stream has not joined yet
 
 
 def _wgrad_stream(device) -> "torch.cuda.Stream":
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=device)
+    _side_pending.add(key)
     return _side_streams[key]
 
 
 def join_wgrad_stream(device, waiter: "torch.cuda.Stream" = None) -> None:
-    """``waiter`` (default: the current stream) waits for every weight-gradient kernel forked from the current stream so far."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
-    side = _side_streams.get(key)
-    if side is not None:
-        (waiter or torch.cuda.current_stream(device)).wait_stream(side)
+    """``waiter`` (default: the current stream) waits for every weight-gradient kernel forked from the current stream so far.
+    A join by the forking stream itself settles the fork (later joins are no-ops until the next wgrad is forked -- which also keeps
+    a CUDA-graph capture from depending on side-stream work enqueued before the capture began)."""
+    cur = torch.cuda.current_stream(device)
+    key = (device, cur.cuda_stream)
+    if key not in _side_pending:
+        return
+    (waiter or cur).wait_stream(_side_streams[key])
+    if waiter is None or waiter.cuda_stream == cur.cuda_stream:
+        _side_pending.discard(key)
 
 
 class _Conv1x1Fn(torch.autograd.Function):
@@ -316,8 +325,13 @@ class _ConvGFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] and WGRAD_SIDE_STREAM:
             side = _wgrad_stream(dy.device)
             side.wait_stream(torch.cuda.current_stream(dy.device))          # dy and x are complete
+            cur = torch.cuda.current_stream(dy.device)
             with torch.cuda.stream(side):
                 dw = wgrad()
+            if not torch.cuda.is_current_stream_capturing():
+                dw.record_stream(cur)              # allocated on the side stream, consumed (and later freed) by the backward stream
+                dy.record_stream(side)             # ... and the other way round for its inputs
+                x.record_stream(side)
         if ctx.needs_input_grad[0]:
             if ctx.halo:
                 dx = conv3x3_halo(dy, weight, True)

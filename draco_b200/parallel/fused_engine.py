@@ -96,7 +96,7 @@ class FusedEngine:
         # one worker on this GPU (the 8-GPU topology): overlap the weight-gradient kernels with the rest of the backward chain
         from ..ops import conv as _conv_ops_mod
         _conv_ops_mod.WGRAD_SIDE_STREAM = (cfg.wgrad_stream == "on" or (cfg.wgrad_stream == "auto" and len(self.local_workers) == 1)) \
-            and not cfg.profile_phases
+            and not cfg.profile_phases and cfg.zero_copy_grads      # stolen gradients only: see ops/conv.py
 
         if cfg.deterministic:
             torch.backends.cudnn.deterministic = True
