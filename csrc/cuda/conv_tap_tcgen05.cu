@@ -20,6 +20,9 @@
 // the stride-2 dgrad parity classes, whose output pixels are strided, keep the direct-store epilogue.
 //
 // Reference counterpart: the strided nn.Conv2d layers of src/model_ops/resnet.py:14-64 (downsampling blocks + shortcuts).
+#include <cstdio>
+#include <cstdlib>
+
 #include "conv_epilogue.cuh"
 #include "tcgen05_common.cuh"
 
@@ -48,6 +51,12 @@ struct TapConvArgs {
   // decreasing tap count (longest tiles first: the static round-robin over CTAs then balances).  Dense launches have one class.
   int nclass;
   int cls_tap0[MAX_CLASSES + 1], cls_oh[MAX_CLASSES], cls_ow[MAX_CLASSES];
+  // Thread-block cluster of cm x cn CTAs working on cm x cn neighbouring tiles (1 x 1 = no cluster).  The cn CTAs of a cluster
+  // row share their activation tile and the cm CTAs of a column their weight tile: every CTA loads 1/cn of A and 1/cm of B and
+  // TMA-multicasts it to the CTAs that need it, so the L2 -> SM traffic of a tile drops from A + B to A/cn + B/cm (these layers
+  // are bound by exactly that traffic: ~150 MB per convolution against ~6300 B/clk of L2 throughput).
+  int cm, cn;
+  int sl_fw, sl_fh;            // the A slice of CTA column rn: split factors of the patch along w and h (n takes the rest)
   __nv_bfloat16* out;          // [N, out_H, out_W, Cn]
   const float* bias_f32;
   const __nv_bfloat16* bias_bf16;
@@ -59,10 +68,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return MN_MAJOR ? desc_mnmajor(smem_addr, BLOCK_K * 128) : desc_kmajor(smem_addr);
 }
 
-template <int BLOCK_N, int STAGES, bool B_MN, bool TMA_EPI>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// tmap_xs / tmap_ws: the same tensors with the SLICE boxes of the cluster variant (1/cn of the patch, 1/cm of the weight rows).
+template <int BLOCK_N, int STAGES, bool B_MN, bool TMA_EPI, bool CLUSTER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                     const __grid_constant__ CUtensorMap tmap_out, const TapConvArgs a) {
+                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_xs,
+                     const __grid_constant__ CUtensorMap tmap_ws, const TapConvArgs a) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -84,18 +104,41 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const int wt = a.OW / a.BW, ht = a.OH / a.BH, nt = (a.N + a.BN - 1) / a.BN;
   const int m_tiles = wt * ht * nt;
   const int n_tiles = (a.Cn + BLOCK_N - 1) / BLOCK_N;
-  const int class_tiles = m_tiles * n_tiles;
-  const int num_tiles = class_tiles * a.nclass;
   const int c_blocks = a.Cred / BLOCK_K;           // 64-channel slices per tap
   const bool want_stats = TMA_EPI && a.stat.partial != nullptr;
+  // Work units: a unit is one tile, or (cluster variant) a super-tile of cm x cn tiles handled by one cluster in lockstep.
+  // Units are numbered class-major; unit -> (class, M super-tile, N super-tile); this CTA takes tile (rm, rn) of the unit.
+  const int cs = CLUSTER ? a.cm * a.cn : 1;
+  const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
+  const int rm = CLUSTER ? crank / a.cn : 0, rn = CLUSTER ? crank % a.cn : 0;
+  const int sn_tiles = CLUSTER ? n_tiles / a.cn : n_tiles;
+  const int class_units = (CLUSTER ? m_tiles / a.cm : m_tiles) * sn_tiles;
+  const int num_units = class_units * a.nclass;
+  const int unit0 = blockIdx.x / cs, unit_step = gridDim.x / cs;
+  auto decode = [&](int unit, int& cls, int& mt, int& n0) {
+    cls = unit / class_units;
+    const int cu = unit - cls * class_units;
+    const int smt = cu / sn_tiles, snt = cu - smt * sn_tiles;
+    mt = CLUSTER ? smt * a.cm + rm : smt;
+    n0 = (CLUSTER ? snt * a.cn + rn : snt) * BLOCK_N;
+  };
+  // multicast masks: the CTAs of my cluster row (they receive my A slice) and of my cluster column (my B slice)
+  uint16_t mask_row = 1, mask_col = 1;
+  if (CLUSTER) {
+    mask_row = (uint16_t)(((1u << a.cn) - 1u) << (rm * a.cn));
+    mask_col = 0;
+    for (int j = 0; j < a.cm; ++j) mask_col |= (uint16_t)(1u << (j * a.cn + rn));
+  }
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_x);
-    prefetch_tmap(&tmap_w);
+    prefetch_tmap(CLUSTER ? &tmap_xs : &tmap_x);
+    prefetch_tmap(CLUSTER ? &tmap_ws : &tmap_w);
     if (TMA_EPI) prefetch_tmap(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // a slot is free again when every CTA that reads what I multicast into it has consumed it: my row and my column
+    const int releases = CLUSTER ? a.cm + a.cn - 1 : 1;
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], releases); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     mbar_fence_init();
   }
@@ -105,6 +148,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();                 // every barrier of the cluster is initialised before anyone signals a peer
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -112,9 +156,15 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int cls = tile / class_tiles, ct = tile - cls * class_tiles;
-        const int mt = ct / n_tiles, n0 = (ct % n_tiles) * BLOCK_N;
+      // cluster variant: my slice of the activation patch (rows [rn * 128/cn, ...) of the tile) and of the weight tile
+      const int a_rows = BLOCK_M / (CLUSTER ? a.cn : 1);
+      const int sl_iw = rn % a.sl_fw, sl_ih = (rn / a.sl_fw) % a.sl_fh, sl_in = rn / (a.sl_fw * a.sl_fh);
+      const int sl_fn = (CLUSTER ? a.cn : 1) / (a.sl_fw * a.sl_fh);
+      const int sl_w = sl_iw * (a.BW / a.sl_fw), sl_h = sl_ih * (a.BH / a.sl_fh), sl_n = sl_in * (a.BN / sl_fn);
+      const int b_rows = (B_MN ? BLOCK_K : BLOCK_N) / (CLUSTER ? a.cm : 1);
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        int cls, mt, n0;
+        decode(unit, cls, mt, n0);
         const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
         const int tap0 = a.cls_tap0[cls], k_blocks = (a.cls_tap0[cls + 1] - tap0) * c_blocks;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -123,14 +173,28 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          // activation patch of this tap: (strided) 4-D box, out-of-range pixels zero-filled by TMA
-          tma_load_4d(sa, &tmap_x, c0, w0 * a.in_mul + a.tap_dw[tap], h0 * a.in_mul + a.tap_dh[tap], nb0, &full_bar[stage]);
-          if (!B_MN) {
-            tma_load_2d(sb, &tmap_w, a.tap_wcol[tap] + c0, n0, &full_bar[stage]);                 // rows = Cout tile, K-major
-          } else {
+          if (!CLUSTER) {
+            // activation patch of this tap: (strided) 4-D box, out-of-range pixels zero-filled by TMA
+            tma_load_4d(sa, &tmap_x, c0, w0 * a.in_mul + a.tap_dw[tap], h0 * a.in_mul + a.tap_dh[tap], nb0, &full_bar[stage]);
+            if (!B_MN) {
+              tma_load_2d(sb, &tmap_w, a.tap_wcol[tap] + c0, n0, &full_bar[stage]);               // rows = Cout tile, K-major
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)                                               // rows = Cout (K), cols = Cin (N)
-              tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_w, a.tap_wcol[tap] + n0 + 64 * j, c0, &full_bar[stage]);
+              for (int j = 0; j < BLOCK_N / 64; ++j)                                             // rows = Cout (K), cols = Cin (N)
+                tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_w, a.tap_wcol[tap] + n0 + 64 * j, c0, &full_bar[stage]);
+            }
+          } else {
+            // the full barrier of EVERY destination CTA (same offset) receives the bytes; each CTA armed its own for A + B
+            tma_load_4d_mc(sa + rn * a_rows * 128, &tmap_xs, c0, (w0 + sl_w) * a.in_mul + a.tap_dw[tap],
+                           (h0 + sl_h) * a.in_mul + a.tap_dh[tap], nb0 + sl_n, &full_bar[stage], mask_row);
+            if (!B_MN) {
+              tma_load_2d_mc(sb + rm * b_rows * 128, &tmap_ws, a.tap_wcol[tap] + c0, n0 + rm * b_rows, &full_bar[stage], mask_col);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d_mc(sb + j * (BLOCK_K * 128) + rm * b_rows * 128, &tmap_ws, a.tap_wcol[tap] + n0 + 64 * j,
+                               c0 + rm * b_rows, &full_bar[stage], mask_col);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -142,8 +206,8 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, false, B_MN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int cls = tile / class_tiles;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        const int cls = unit / class_units;
         const int k_blocks = (a.cls_tap0[cls + 1] - a.cls_tap0[cls]) * c_blocks;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -160,7 +224,8 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const uint64_t adv_b = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
             umma_f16(tmem_d, da + adv_a, db + adv_b, idesc, (kb | k) ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[stage]);
+          if (CLUSTER) tcgen05_commit_mc(&empty_bar[stage], mask_row | mask_col);   // release the slot at every CTA that fills it
+          else tcgen05_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(&tmem_full[acc]);
@@ -175,11 +240,11 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     convepi::StatAcc<BLOCK_N> sacc;
     sacc.clear();
     // every tile of this CTA covers the same channels (one N tile, or one tile per CTA): statistics stay in registers until the end
-    const bool stat_keep = n_tiles == 1 || num_tiles <= (int)gridDim.x;
+    const bool stat_keep = sn_tiles == 1 || num_units <= unit_step;
     int stat_col0 = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int cls = tile / class_tiles, ct = tile - cls * class_tiles;
-      const int mt = ct / n_tiles, n0 = (ct % n_tiles) * BLOCK_N;
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      int cls, mt, n0;
+      decode(unit, cls, mt, n0);
       const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -240,11 +305,13 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();                 // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
   if (want_stats) {
-    // one tile per CTA (tiles <= grid): slot = M tile, this CTA owns its N-tile's channels; otherwise slot = CTA, all channels
-    const bool one_tile = num_tiles <= (int)gridDim.x;
-    const int mt = blockIdx.x / n_tiles, n0 = (blockIdx.x % n_tiles) * BLOCK_N;
+    // one tile per CTA (units <= clusters): slot = M tile, this CTA owns its N-tile's channels; otherwise slot = CTA, all channels
+    const bool one_tile = num_units <= unit_step;
+    int cls0, mt, n0;
+    decode(unit0, cls0, mt, n0);
     const int c_hi = n0 + BLOCK_N < a.Cn ? n0 + BLOCK_N : a.Cn;
     convepi::finalize_stats<NUM_THREADS>(a.stat, s_stat, convepi::STAT_PARTS, a.Cn, one_tile ? mt : (int)blockIdx.x,
                                          one_tile ? m_tiles : (int)gridDim.x, one_tile ? n0 : 0, one_tile ? c_hi : a.Cn,
@@ -418,32 +485,39 @@ __global__ void wgradg_reduce_kernel(const float* partial, int splits, long long
   *reinterpret_cast<uint2*>(out + i) = o;
 }
 
-template <int BLOCK_N, bool B_MN, bool TMA_EPI>
-int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const TapConvArgs& a, int num_sms, cudaStream_t stream) {
+template <int BLOCK_N, bool B_MN, bool TMA_EPI, bool CLUSTER>
+int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const CUtensorMap& txs, const CUtensorMap& tws,
+             const TapConvArgs& a, int grid, cudaStream_t stream) {
   constexpr int STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2;
   constexpr int EPI_BYTES = TMA_EPI ? convepi::staging_bytes(BLOCK_N) + convepi::stat_bytes() : 0;
   constexpr int BUDGET = 200 * 1024 - EPI_BYTES;
   constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
-  auto kern = convg_tcgen05_kernel<BLOCK_N, STAGES, B_MN, TMA_EPI>;
+  auto kern = convg_tcgen05_kernel<BLOCK_N, STAGES, B_MN, TMA_EPI, CLUSTER>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int m_tiles = (a.OW / a.BW) * (a.OH / a.BH) * ((a.N + a.BN - 1) / a.BN);
-  const int tiles = m_tiles * ((a.Cn + BLOCK_N - 1) / BLOCK_N) * a.nclass;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, SMEM, stream>>>(tx, tw, tout, a);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CLUSTER ? a.cm * a.cn : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = CLUSTER ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, tout, txs, tws, a);
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 template <bool B_MN, bool TMA_EPI>
-int launch_n(int block_n, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const TapConvArgs& a, int num_sms,
-             cudaStream_t stream) {
-  return block_n == 64 ? launch_g<64, B_MN, TMA_EPI>(tx, tw, tout, a, num_sms, stream)
-                       : launch_g<128, B_MN, TMA_EPI>(tx, tw, tout, a, num_sms, stream);
+int launch_n(int block_n, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const CUtensorMap& txs,
+             const CUtensorMap& tws, const TapConvArgs& a, int grid, cudaStream_t stream) {
+  if (a.cm * a.cn > 1)
+    return block_n == 64 ? launch_g<64, B_MN, TMA_EPI, true>(tx, tw, tout, txs, tws, a, grid, stream)
+                         : launch_g<128, B_MN, TMA_EPI, true>(tx, tw, tout, txs, tws, a, grid, stream);
+  return block_n == 64 ? launch_g<64, B_MN, TMA_EPI, false>(tx, tw, tout, txs, tws, a, grid, stream)
+                       : launch_g<128, B_MN, TMA_EPI, false>(tx, tw, tout, txs, tws, a, grid, stream);
 }
 
 // patch shape for an iteration space of OH x OW pixels per image: BW * BH * BN == pixels with BW | OW and BH | OH (the largest
@@ -458,6 +532,72 @@ void patch_shape(int OH, int OW, int pixels, int& BW, int& BH, int& BN) {
   BW = pow2_divisor(OW, pixels);
   BH = pow2_divisor(OH, pixels / BW);
   BN = pixels / (BW * BH);
+}
+
+// Tile width, cluster shape and grid of one launch.
+//
+// MEASURED (profiles/conv_cluster_sweep.md, B200, ResNet-18 layers at B=128): the multicast cluster variant reproduces the plain
+// kernel bit for bit but is never faster -- 2-CTA clusters cost +5..10 %, 4-CTA +10..40 %, 8-CTA clusters 2x (only half of them
+// become co-resident next to 1-CTA/SM, 200 KB kernels).  These layers are bound by the bytes DELIVERED to the SMs (~6300 B/clk
+// chip-wide, B300_MICROARCH.md "LTS throughput cap"; TMA multicast at cluster size <= 4 does not lower that), so the default plan
+// is cm = cn = 1 with the tile width chosen by the model below; DRACO_CONV_CLUSTER="cm,cn[,block_n]" forces a cluster shape
+// ("auto" lets the model pick one) for experiments and for the tests that keep the multicast path honest.
+// Model: a tile costs k_blocks * (A/cn + B/cm) bytes of L2 -> SM traffic and k_blocks * 4 MMAs of BLOCK_N/2 clocks.
+struct TapPlan { int block_n, cm, cn, grid, units; };
+
+int clusters_resident(int cs, int num_sms) {
+  // GPCs of a B200 expose 16-20 SMs each and a cluster never spans GPCs: count conservatively
+  if (cs <= 1) return num_sms;
+  if (cs == 2) return num_sms / 2 - 2;
+  if (cs == 4) return num_sms / 4 - 3;
+  return num_sms / 8 - 2;
+}
+
+TapPlan plan_tap(int m_tiles, int Cn, int k_blocks_total, int nclass, bool b_mn, int num_sms) {
+  int f_cm = 1, f_cn = 1, f_bn = Cn >= 128 ? 128 : 64;          // default: no cluster, 128-wide tiles when the layer has them
+  if (const char* e = getenv("DRACO_CONV_CLUSTER")) {
+    int x = 0, y = 0, z = 0;
+    const int got = sscanf(e, "%d,%d,%d", &x, &y, &z);
+    if (got >= 2) { f_cm = x; f_cn = y; f_bn = -1; }
+    else if (e[0] == 'a') { f_cm = f_cn = f_bn = -1; }
+    if (got >= 3) f_bn = z;
+  }
+  TapPlan best = {Cn >= 128 ? 128 : 64, 1, 1, 0, 0};
+  double best_t = 1e30;
+  for (int bn = 128; bn >= 64; bn -= 64) {
+    if (bn > Cn && bn != 64) continue;
+    if (f_bn > 0 && bn != f_bn) continue;
+    const int n_tiles = (Cn + bn - 1) / bn;
+    for (int cm = 1; cm <= 8; cm *= 2) {
+      for (int cn = 1; cm * cn <= 8; cn *= 2) {
+        if (f_cm > 0 && (cm != f_cm || cn != f_cn)) continue;
+        if (m_tiles % cm || n_tiles % cn) continue;
+        if ((b_mn ? BLOCK_K : bn) / cm < 8 || BLOCK_M / cn < 8) continue;
+        if (Cn % bn && cm * cn > 1) continue;                       // partial N tiles only without clusters
+        const int cs = cm * cn;
+        const long long units = (long long)(m_tiles / cm) * (n_tiles / cn) * nclass;
+        const long long clusters = units < clusters_resident(cs, num_sms) ? units : clusters_resident(cs, num_sms);
+        const double waves = (double)((units + clusters - 1) / clusters);
+        const double kb = (double)k_blocks_total / nclass;          // mean K blocks of a tile
+        const double tile_bytes = kb * (16384.0 / cn + bn * 128.0 / cm);
+        const double t_mma = waves * kb * 4 * (bn / 2);
+        const double t_sm = waves * tile_bytes / 64.0;
+        const double t_chip = (double)units * cs * tile_bytes / 6300.0;
+        double t = t_mma > t_sm ? t_mma : t_sm;
+        if (t_chip > t) t = t_chip;
+        t += waves * 600 + (cs > 1 ? 400 : 0);                      // epilogue tail per wave, cluster launch + syncs
+        if (t < best_t) { best_t = t; best = {bn, cm, cn, (int)(clusters * cs), (int)units}; }
+      }
+    }
+  }
+  return best;
+}
+
+// slice boxes of the cluster variant: the patch BW x BH x BN split cn ways along n, then h, then w (rows of a slice stay contiguous)
+void slice_shape(int BW, int BH, int BN, int cn, int& fw, int& fh, int& fn) {
+  fn = cn < BN ? cn : BN;
+  fh = cn / fn < BH ? cn / fn : BH;
+  fw = cn / (fn * fh);
 }
 
 }  // namespace
@@ -501,13 +641,29 @@ extern "C" int drc_convg_supported(int H, int W, int Cin, int Cout, int ks, int 
 // stat_*: optional BatchNorm statistics of y (fprop + TMA-store epilogue only): workspace of drc_convg_stat_slots() * 2 * Cout
 // floats, a zeroed ticket counter, outputs mean / invstd [Cout], optional running statistics (momentum update).
 extern "C" int drc_convg_stat_slots(int N, int H, int W, int Cout, int stride, int num_sms) {
+  // the number of partial-statistics slots only has to be an upper bound of what the launch uses (one slot per M tile when every
+  // tile has its own CTA, one per CTA otherwise); the kernel is told the exact number
   const int OH = H / stride, OW = W / stride;
   int BW, BH, BN;
   patch_shape(OH, OW, BLOCK_M, BW, BH, BN);
   const int m_tiles = (OW / BW) * (OH / BH) * ((N + BN - 1) / BN);
-  const int block_n = Cout >= 128 ? 128 : 64;
-  const int tiles = m_tiles * ((Cout + block_n - 1) / block_n);
-  return tiles <= num_sms ? m_tiles : num_sms;
+  return m_tiles > num_sms ? m_tiles : num_sms;
+}
+
+// Test hook: the plan (block_n, cm, cn, grid) the launcher would use.
+extern "C" int drc_convg_plan(int N, int H, int W, int Cin, int Cout, int ks, int stride, int dgrad, int num_sms, int* out4) {
+  if (!drc_convg_supported(H, W, Cin, Cout, ks, stride)) return -1;
+  const int OH = H / stride, OW = W / stride;
+  int BW, BH, BN;
+  patch_shape(OH, OW, BLOCK_M, BW, BH, BN);
+  const int m_tiles = (OW / BW) * (OH / BH) * ((N + BN - 1) / BN);
+  const int Cred = dgrad ? Cout : Cin, Cn = dgrad ? Cin : Cout;
+  const bool strided_dgrad = dgrad && stride > 1;
+  int nclass = 1, ntaps = ks * ks;
+  if (strided_dgrad) { nclass = ks == 1 ? 1 : stride * stride; ntaps = ks * ks; }
+  const TapPlan p = plan_tap(m_tiles, Cn, ntaps * (Cred / BLOCK_K), nclass, dgrad != 0, num_sms);
+  out4[0] = p.block_n; out4[1] = p.cm; out4[2] = p.cn; out4[3] = p.grid;
+  return 0;
 }
 
 extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int H, int W, int Cin, int Cout, int ks, int stride,
@@ -525,73 +681,77 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   a.stat.partial = nullptr; a.stat.counter = stat_counter; a.stat.mean = stat_mean; a.stat.invstd = stat_invstd;
   a.stat.running_mean = running_mean; a.stat.running_var = running_var; a.stat.count = (long long)N * OH * OW;
   a.stat.eps = eps; a.stat.momentum = momentum;
-  const int block_n = a.Cn >= 128 ? 128 : 64;
   const bool dense_out = !(dgrad && stride > 1);
   const bool tma_epi = tma_store && dense_out;
   if (stat_partial) {
     if (dgrad || !tma_epi || Cout > convepi::STAT_MAX_C || (Cout & 3)) return -4;
     a.stat.partial = stat_partial;
   }
-  CUtensorMap tx, tw, tout;
-  // weights as a matrix [Cout rows][ks*ks*Cin cols]
-  int r = encode_mat(&tw, wgt, Cout, (long long)ks * ks * Cin, (long long)ks * ks * Cin, dgrad ? BLOCK_K : block_n);
+  const int m_tiles = (OW / a.BW) * (OH / a.BH) * ((N + a.BN - 1) / a.BN);
+
+  // ---- tap table (+ output classes)
+  a.in_mul = dgrad ? 1 : stride;
+  a.out_H = dgrad ? H : OH; a.out_W = dgrad ? W : OW; a.out_mul = dgrad ? stride : 1;
+  if (dgrad) { a.bias_f32 = nullptr; a.bias_bf16 = nullptr; }
+  if (dense_out) {
+    int tidx[MAX_TAPS];
+    a.ntaps = drc_convg_taps(ks, dgrad ? 1 : stride, dgrad, 0, 0, a.tap_dh, a.tap_dw, tidx);
+    for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
+    a.nclass = 1; a.cls_tap0[0] = 0; a.cls_tap0[1] = a.ntaps; a.cls_oh[0] = a.cls_ow[0] = 0;
+  } else {
+    // stride 2 dgrad: the s x s parity classes of dx in ONE launch (class-major unit list, longest classes first)
+    struct Cls { int ph, pw, n, dh[MAX_TAPS], dw[MAX_TAPS], tidx[MAX_TAPS]; } cls[MAX_CLASSES];
+    int nc = 0, empty = 0;
+    for (int ph = 0; ph < stride; ++ph)
+      for (int pw = 0; pw < stride; ++pw) {
+        Cls c; c.ph = ph; c.pw = pw;
+        c.n = drc_convg_taps(ks, stride, 1, ph, pw, c.dh, c.dw, c.tidx);
+        if (c.n == 0) { ++empty; continue; }
+        int at = nc++;
+        while (at > 0 && cls[at - 1].n < c.n) { cls[at] = cls[at - 1]; --at; }
+        cls[at] = c;
+      }
+    if (empty) {                                  // classes that receive nothing (1x1 / stride 2) have to read as zero
+      cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * H * W * Cin * 2, stream);
+      if (e != cudaSuccess) return (int)e;
+    }
+    a.nclass = nc; a.ntaps = 0;
+    for (int c = 0; c < nc; ++c) {
+      a.cls_tap0[c] = a.ntaps; a.cls_oh[c] = cls[c].ph; a.cls_ow[c] = cls[c].pw;
+      for (int t = 0; t < cls[c].n; ++t, ++a.ntaps) {
+        a.tap_dh[a.ntaps] = cls[c].dh[t]; a.tap_dw[a.ntaps] = cls[c].dw[t]; a.tap_wcol[a.ntaps] = cls[c].tidx[t] * Cin;
+      }
+    }
+    a.cls_tap0[nc] = a.ntaps;
+  }
+
+  // ---- plan + tensor maps
+  const TapPlan plan = plan_tap(m_tiles, a.Cn, a.ntaps * (a.Cred / BLOCK_K), a.nclass, dgrad != 0, num_sms);
+  const int block_n = plan.block_n;
+  a.cm = plan.cm; a.cn = plan.cn;
+  int fw = 1, fh = 1, fn = 1;
+  slice_shape(a.BW, a.BH, a.BN, a.cn, fw, fh, fn);
+  a.sl_fw = fw; a.sl_fh = fh;
+  CUtensorMap tx, tw, tout, txs, tws;
+  const long long wcols = (long long)ks * ks * Cin;               // weights as a matrix [Cout rows][ks*ks*Cin cols]
+  int r = encode_mat(&tw, wgt, Cout, wcols, wcols, dgrad ? BLOCK_K : block_n);
   if (r) return 2000 + r;
-  tout = tw;                                      // placeholder when the direct epilogue is used (never dereferenced)
-  if (!dgrad) {
-    r = encode_act(&tx, act, Cin, W, H, N, a.BW, a.BH, a.BN, stride);
-    if (r) return 1000 + r;
-    int tidx[MAX_TAPS];
-    a.in_mul = stride;
-    a.ntaps = drc_convg_taps(ks, stride, 0, 0, 0, a.tap_dh, a.tap_dw, tidx);
-    for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
-    a.out_H = OH; a.out_W = OW; a.out_mul = 1;
-    a.nclass = 1; a.cls_tap0[0] = 0; a.cls_tap0[1] = a.ntaps; a.cls_oh[0] = a.cls_ow[0] = 0;
-    if (tma_epi) {
-      r = encode_act(&tout, out, Cout, OW, OH, N, a.BW, a.BH, a.BN, 1);
-      if (r) return 3000 + r;
-      return launch_n<false, true>(block_n, tx, tw, tout, a, num_sms, stream);
-    }
-    return launch_n<false, false>(block_n, tx, tw, tout, a, num_sms, stream);
-  }
-  // dgrad: dy has OH x OW pixels per image and is read with unit stride
-  r = encode_act(&tx, act, Cout, OW, OH, N, a.BW, a.BH, a.BN, 1);
+  r = encode_mat(&tws, wgt, Cout, wcols, wcols, (dgrad ? BLOCK_K : block_n) / a.cm);
+  if (r) return 2100 + r;
+  const int aC = dgrad ? Cout : Cin, aW = dgrad ? OW : W, aH = dgrad ? OH : H, aS = dgrad ? 1 : stride;
+  r = encode_act(&tx, act, aC, aW, aH, N, a.BW, a.BH, a.BN, aS);
   if (r) return 1000 + r;
-  a.in_mul = 1; a.out_H = H; a.out_W = W; a.out_mul = stride;
-  a.bias_f32 = nullptr; a.bias_bf16 = nullptr;
-  if (tma_epi) {                                  // stride 1: one dense launch
-    int tidx[MAX_TAPS];
-    a.ntaps = drc_convg_taps(ks, 1, 1, 0, 0, a.tap_dh, a.tap_dw, tidx);
-    for (int t = 0; t < a.ntaps; ++t) a.tap_wcol[t] = tidx[t] * Cin;
-    a.nclass = 1; a.cls_tap0[0] = 0; a.cls_tap0[1] = a.ntaps; a.cls_oh[0] = a.cls_ow[0] = 0;
-    r = encode_act(&tout, out, Cin, W, H, N, a.BW, a.BH, a.BN, 1);
+  r = encode_act(&txs, act, aC, aW, aH, N, a.BW / fw, a.BH / fh, a.BN / fn, aS);
+  if (r) return 1100 + r;
+  tout = tw;                                      // placeholder when the direct epilogue is used (never dereferenced)
+  if (tma_epi) {
+    r = encode_act(&tout, out, a.Cn, a.out_W, a.out_H, N, a.BW, a.BH, a.BN, 1);
     if (r) return 3000 + r;
-    return launch_n<true, true>(block_n, tx, tw, tout, a, num_sms, stream);
   }
-  // stride 2: the s x s parity classes of dx in ONE launch (class-major tile list, longest classes first)
-  struct Cls { int ph, pw, n, dh[MAX_TAPS], dw[MAX_TAPS], tidx[MAX_TAPS]; } cls[MAX_CLASSES];
-  int nc = 0, empty = 0;
-  for (int ph = 0; ph < stride; ++ph)
-    for (int pw = 0; pw < stride; ++pw) {
-      Cls c; c.ph = ph; c.pw = pw;
-      c.n = drc_convg_taps(ks, stride, 1, ph, pw, c.dh, c.dw, c.tidx);
-      if (c.n == 0) { ++empty; continue; }
-      int at = nc++;
-      while (at > 0 && cls[at - 1].n < c.n) { cls[at] = cls[at - 1]; --at; }
-      cls[at] = c;
-    }
-  if (empty) {                                    // classes that receive nothing (1x1 / stride 2) have to read as zero
-    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * H * W * Cin * 2, stream);
-    if (e != cudaSuccess) return (int)e;
-  }
-  a.nclass = nc; a.ntaps = 0;
-  for (int c = 0; c < nc; ++c) {
-    a.cls_tap0[c] = a.ntaps; a.cls_oh[c] = cls[c].ph; a.cls_ow[c] = cls[c].pw;
-    for (int t = 0; t < cls[c].n; ++t, ++a.ntaps) {
-      a.tap_dh[a.ntaps] = cls[c].dh[t]; a.tap_dw[a.ntaps] = cls[c].dw[t]; a.tap_wcol[a.ntaps] = cls[c].tidx[t] * Cin;
-    }
-  }
-  a.cls_tap0[nc] = a.ntaps;
-  return launch_n<true, false>(block_n, tx, tw, tout, a, num_sms, stream);
+  if (!dgrad) return tma_epi ? launch_n<false, true>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream)
+                             : launch_n<false, false>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream);
+  return tma_epi ? launch_n<true, true>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream)
+                 : launch_n<true, false>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream);
 }
 
 namespace {

@@ -21,6 +21,7 @@ from torch import nn
 from ..ops.conv import Conv2d
 from ..ops.linear import Linear
 from ..ops.norm import FusedBatchNorm2d
+from ..ops.pool import global_avg_pool
 from .split import make_split
 
 
@@ -111,8 +112,7 @@ class ResNet(nn.Module):
         if self.imagenet_stem:
             out = F.max_pool2d(out, kernel_size=3, stride=2, padding=1)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
-        out = F.adaptive_avg_pool2d(out, 1) if out.shape[-1] != 4 else F.avg_pool2d(out, 4)
-        return self.linear(out.flatten(1))
+        return self.linear(global_avg_pool(out))          # == F.avg_pool2d(out, 4) on the reference's 4x4 maps
 
     def name(self) -> str:
         return "resnet"

@@ -83,6 +83,8 @@ def _lib():
         lib.drc_convg_supported.restype = C.c_int
         lib.drc_convg_stat_slots.argtypes = [C.c_int] * 6
         lib.drc_convg_stat_slots.restype = C.c_int
+        lib.drc_convg_plan.argtypes = [C.c_int] * 9 + [C.POINTER(C.c_int)]
+        lib.drc_convg_plan.restype = C.c_int
         lib.drc_convg.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 8 + [N.ptr, N.ptr, C.c_int] + [N.ptr] * 6
                                   + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
         lib.drc_convg.restype = C.c_int
@@ -166,6 +168,15 @@ def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, d
                           tma, *st, sms, act.device.index, torch.cuda.current_stream().cuda_stream), "convg")
     del keep
     return out
+
+
+def convg_plan(n: int, h: int, w: int, cin: int, cout: int, ks: int, stride: int, dgrad: int, num_sms: int = 148):
+    """[block_n, cm, cn, grid] the tap-convolution launcher picks for this layer (host-side planning only; no GPU needed)."""
+    import ctypes as C
+    out = (C.c_int * 4)()
+    if _lib().drc_convg_plan(n, h, w, cin, cout, ks, stride, int(dgrad), num_sms, out) != 0:
+        return None
+    return list(out)
 
 
 def convg_wgrad_tcgen05(dy: torch.Tensor, x: torch.Tensor, ks: int, stride: int) -> torch.Tensor:

@@ -52,9 +52,8 @@ class _LinearFn(torch.autograd.Function):
             # narrow heads (10 classes): a row of dy / a column block of W is not a 16-byte multiple, which TMA requires.  Pad the
             # class dimension with zeros to the next multiple of 8 (two tiny copies) and stay on the tensor-core kernel.
             pad = 8 - nout % 8
-            dy_p = F.pad(dy2, (0, pad))
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = dy2.sum(0)
+            from .pool import head_prep
+            dy_p, db = head_prep(dy2, nout + pad, ctx.has_bias and ctx.needs_input_grad[2])     # pad + bias gradient, one launch
             if ctx.needs_input_grad[0]:
                 backend_counters["tcgen05"] += 1
                 dx = K.gemm_bf16(dy_p, F.pad(weight, (0, 0, 0, pad)), b_mn=True)

@@ -406,6 +406,8 @@ class FusedEngine:
                         flag = self.grad_flag_ptr(_w) if _state["done"] == nb else None
                     # remote slot: NVLink-bound, few CTAs; local slot (PS on this GPU): HBM-bound, 2 CTAs per SM
                     grid = self.cfg.push_ctas if self.rank != 0 else 2 * K.sm_count()
+                    if _state["done"] == nb and len(self.local_workers) == 1:
+                        grid = max(grid, K.sm_count())        # last bucket of the only worker: backward is over, nothing to starve
                     K.push_encode(L, _g32, _g16, self.slot_ptr(_w), tile_range=(t0, t1), grid=min(grid, t1 - t0),
                                   flag=flag, **_kw)
 

@@ -475,3 +475,37 @@ def test_replica_dropout_is_keyed_by_device_step_and_graph_safe():
     D.clear_context()
     step.fill_(2)
     assert torch.equal(run(l1, 3)[0], y2)
+
+
+@pytest.mark.parametrize("n,c,hw", [(128, 512, 4), (6, 2048, 7), (3, 64, 1), (17, 256, 5)])
+def test_global_avg_pool_kernels(n, c, hw):
+    """Global average pool forward / backward on channels-last bf16 (csrc/cuda/pool_head.cu) vs fp32 torch."""
+    from draco_b200.ops.pool import backend_counters, global_avg_pool
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(n + c)
+    x = torch.randn(n, c, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    before = backend_counters["native"]
+    y = global_avg_pool(x)
+    assert backend_counters["native"] == before + 1 and y.shape == (n, c)
+    ref = x.detach().float().mean((2, 3))
+    assert (y.float() - ref).abs().max() <= 1e-2 * ref.abs().max() + 1e-3
+    gy = torch.randn(n, c, device=dev).to(torch.bfloat16)
+    y.backward(gy)
+    gref = (gy.float() / (hw * hw))[:, :, None, None].expand(n, c, hw, hw)
+    assert x.grad.shape == x.shape and x.grad.is_contiguous(memory_format=torch.channels_last)
+    assert (x.grad.float() - gref).abs().max() <= 1e-2 * gref.abs().max() + 1e-6
+    # fp32 / non-channels-last inputs take the library path with the same result
+    assert torch.allclose(global_avg_pool(x.detach().float()), ref, atol=1e-5)
+
+
+def test_narrow_head_backward_prep_kernel():
+    """dy zero-padded to a 16-byte row + bias gradient in one launch (the 10-class Linear backward)."""
+    from draco_b200.ops.pool import head_prep
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    dy = torch.randn(128, 10, device=dev).to(torch.bfloat16)
+    dyp, db = head_prep(dy, 16, True)
+    assert torch.equal(dyp[:, :10], dy) and torch.count_nonzero(dyp[:, 10:]) == 0
+    assert (db.float() - dy.float().sum(0)).abs().max() < 0.1
+    assert torch.equal(head_prep(dy, 16, True)[1], db)
+    assert head_prep(dy, 16, False)[1] is None
