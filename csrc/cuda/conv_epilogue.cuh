@@ -45,7 +45,8 @@ __host__ __device__ constexpr int stat_bytes() { return 4 * 2 * STAT_MAX_C * 4; 
 //   valid_rows: rows of the tile that are real pixels (partial batch tiles), col0: first output channel of the tile
 template <int BLOCK_N>
 __device__ __forceinline__ void drain_tile(uint32_t tmem_acc, uint8_t* sbuf, float* s_stat, int et, int valid_rows, int col0, int Cn,
-                                           const float* bias_f32, const __nv_bfloat16* bias_bf16, uint64_t* tmem_empty_bar) {
+                                           const float* bias_f32, const __nv_bfloat16* bias_bf16, uint64_t* tmem_empty_bar,
+                                           uint32_t remote_empty_bar = 0) {
   const int q = et >> 5, lane = et & 31;
   // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
   if (et == 0) tc::tma_store_wait_read<0>();
@@ -75,7 +76,10 @@ __device__ __forceinline__ void drain_tile(uint32_t tmem_acc, uint8_t* sbuf, flo
   // TMEM fully read by this warp -> the MMA warp may reuse the accumulator
   tc::tcgen05_fence_before();
   __syncwarp();
-  if (lane == 0) tc::mbar_arrive(tmem_empty_bar);
+  if (lane == 0) {
+    if (remote_empty_bar) tc::remote_arrive(remote_empty_bar);     // CTA pair: the barrier lives in the leader CTA
+    else tc::mbar_arrive(tmem_empty_bar);
+  }
   tc::fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
   tc::named_bar_sync(EPI_BAR_ID, EPI_THREADS);
   (void)valid_rows; (void)s_stat;
@@ -137,40 +141,50 @@ constexpr int STAT_PARTS = 4;             // one accumulator row per epilogue wa
 //   c_lo, c_hi   : channel range this CTA writes into its slot (the others in the slot are written by sibling CTAs or are zero)
 template <int NUM_THREADS>
 __device__ __forceinline__ void finalize_stats(const BnStatArgs& st, float* s_stat, int parts, int Cn, int slot, int nslots,
-                                               int c_lo, int c_hi, float* s_scratch /* >= NUM_THREADS * 4 floats */) {
+                                               int c_lo, int c_hi, float* s_scratch /* >= NUM_THREADS * 4 floats */,
+                                               int ticket = 0, int ticket_arrivals = -1) {
+  // This CTA's partial sums of channels [c_lo, c_hi) go to slot `slot`; the LAST of the `ticket_arrivals` CTAs that share ticket
+  // counter `ticket` (all CTAs of the grid, or the CTAs of one channel tile when every tile has its own CTA) folds the nslots
+  // partials of those channels in a fixed order and publishes mean / invstd (+ running statistics).
   __shared__ int s_is_last;
-  for (int i = threadIdx.x; i < 2 * (c_hi - c_lo); i += NUM_THREADS) {
-    const int a = i / (c_hi - c_lo), c = c_lo + i % (c_hi - c_lo);
+  const int width = c_hi - c_lo;                   // multiple of 4
+  for (int i = threadIdx.x; i < 2 * width; i += NUM_THREADS) {
+    const int a = i / width, c = c_lo + i % width;
     float t = 0.f;
     for (int p = 0; p < parts; ++p) t += s_stat[(p * 2 + a) * STAT_MAX_C + c];
     st.partial[((long long)slot * 2 + a) * Cn + c] = t;
   }
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(st.counter, 1u);
-    s_is_last = (prev == gridDim.x - 1);
-    if (s_is_last) *st.counter = 0;
+    // release: the partial stores of the whole CTA (ordered before this thread by the barrier) become visible with the ticket;
+    // acquire: the last CTA sees every other CTA's partials.  One acq_rel atomic instead of two gpu-scope fences around a relaxed one.
+    unsigned int prev;
+    unsigned int* ctr = st.counter + ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ctr) : "memory");
+    const unsigned int last = (unsigned int)(ticket_arrivals < 0 ? (int)gridDim.x : ticket_arrivals) - 1u;
+    s_is_last = (prev == last);
+    if (s_is_last) *ctr = 0;
   }
   __syncthreads();
   if (!s_is_last) return;
-  __threadfence();
-  // fold: items4 = 2C/4 float4 columns, SUB interleaved subsets of the slots; fixed order everywhere
-  const int items4 = (2 * Cn) >> 2;
+  // fold: items4 = 2 * width / 4 float4 columns, SUB interleaved subsets of the slots; fixed order everywhere
+  const int w4 = width >> 2;
+  const int items4 = 2 * w4;
   const int SUB = NUM_THREADS / items4 > 0 ? NUM_THREADS / items4 : 1;
-  const float4* p4 = reinterpret_cast<const float4*>(st.partial);
-  for (int i0 = 0; i0 < items4; i0 += NUM_THREADS) {                 // one pass unless 2C/4 > NUM_THREADS
+  for (int i0 = 0; i0 < items4; i0 += NUM_THREADS) {                 // one pass unless 2 * width / 4 > NUM_THREADS
     const int item = i0 + (int)threadIdx.x % (items4 < NUM_THREADS ? items4 : NUM_THREADS);
     const int sub = items4 < NUM_THREADS ? (int)threadIdx.x / items4 : 0;
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sub < SUB && item < items4) {
-      constexpr int FB = 16;                                          // independent 16-byte loads in flight
+      const int a = item / w4, c4 = item - a * w4;
+      const float* col = st.partial + (long long)a * Cn + c_lo + c4 * 4;          // + slot * 2 * Cn
+      constexpr int FB = 32;                                          // independent 16-byte loads in flight
       for (int g0 = sub; g0 < nslots; g0 += FB * SUB) {
         float4 v[FB];
 #pragma unroll
         for (int u = 0; u < FB; ++u) {
           const int g = g0 + u * SUB;
-          v[u] = g < nslots ? __ldcg(p4 + (long long)g * items4 + item) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u] = g < nslots ? __ldcg(reinterpret_cast<const float4*>(col + (long long)g * 2 * Cn)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < FB; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }      // fixed order
@@ -179,7 +193,7 @@ __device__ __forceinline__ void finalize_stats(const BnStatArgs& st, float* s_st
     __syncthreads();
     reinterpret_cast<float4*>(s_scratch)[threadIdx.x] = t;
     __syncthreads();
-    // subset 0 combines the subsets in order and leaves the totals in s_stat[0 .. 2C)
+    // subset 0 combines the subsets in order and leaves the totals in s_stat: [2][width], a-major
     if (sub == 0 && item < items4) {
       float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
       const int nsub = items4 < NUM_THREADS ? SUB : 1;
@@ -187,14 +201,15 @@ __device__ __forceinline__ void finalize_stats(const BnStatArgs& st, float* s_st
         const float4 v = reinterpret_cast<const float4*>(s_scratch)[s2 * items4 + (item - i0)];
         tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
       }
-      reinterpret_cast<float4*>(s_stat)[item] = tot;                 // s_stat reused: [2][C] totals, a-major
+      reinterpret_cast<float4*>(s_stat)[item] = tot;
     }
   }
   __syncthreads();
   const float inv_m = 1.0f / (float)st.count;
-  for (int c = threadIdx.x; c < Cn; c += NUM_THREADS) {
-    const float m = s_stat[c] * inv_m;
-    float var = fmaf(-m, m, s_stat[Cn + c] * inv_m);
+  for (int i = threadIdx.x; i < width; i += NUM_THREADS) {
+    const int c = c_lo + i;
+    const float m = s_stat[i] * inv_m;
+    float var = fmaf(-m, m, s_stat[width + i] * inv_m);
     var = var < 0.f ? 0.f : var;
     st.mean[c] = m;
     st.invstd[c] = rsqrtf(var + st.eps);

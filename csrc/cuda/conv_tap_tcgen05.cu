@@ -56,6 +56,7 @@ struct TapConvArgs {
   // TMA-multicasts it to the CTAs that need it, so the L2 -> SM traffic of a tile drops from A + B to A/cn + B/cm (these layers
   // are bound by exactly that traffic: ~150 MB per convolution against ~6300 B/clk of L2 throughput).
   int cm, cn;
+  long long* dbg;              // optional per-CTA timeline (8 x int64, tools/prof_conv_timeline.py): null in production
   int sl_fw, sl_fh;            // the A slice of CTA column rn: split factors of the patch along w and h (n takes the rest)
   __nv_bfloat16* out;          // [N, out_H, out_W, Cn]
   const float* bias_f32;
@@ -68,23 +69,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return MN_MAJOR ? desc_mnmajor(smem_addr, BLOCK_K * 128) : desc_kmajor(smem_addr);
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// MODE 0: one CTA per tile.  MODE 1: multicast cluster (see TapConvArgs::cm).  MODE 2: CTA PAIR -- the two CTAs of a cluster
+// execute ONE tcgen05.mma.cta_group::2 of M = 256 over two neighbouring M tiles: each CTA stages its own activation patch and
+// HALF of the weight tile, the tensor cores of both SMs read both halves, so the bytes delivered per SM and K block drop from
+// A + B to A + B/2 (the quantity these layers are bound by); the accumulator of each CTA's 128 rows stays in its own TMEM and
+// the epilogue is unchanged.  Protocol as in gemm2_tcgen05.cu: both producers' loads complete on the LEADER's full barrier
+// (leader-only expect_tx of both CTAs' bytes), the leader issues the MMAs and tcgen05.commit multicasts the stage release /
+// accumulator-ready signal to both CTAs, all eight epilogue warps arrive on the leader's tmem_empty barrier.
+// tmap_xs / tmap_ws: the same tensors with the SLICE boxes (MODE 1: 1/cn of the patch, 1/cm of the weight rows; MODE 2: tmap_ws =
+// half of the weight rows).
+constexpr int MODE_PLAIN = 0, MODE_MCAST = 1, MODE_PAIR = 2;
 
-// tmap_xs / tmap_ws: the same tensors with the SLICE boxes of the cluster variant (1/cn of the patch, 1/cm of the weight rows).
-template <int BLOCK_N, int STAGES, bool B_MN, bool TMA_EPI, bool CLUSTER>
+template <int BLOCK_N, int STAGES, bool B_MN, bool TMA_EPI, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_xs,
                      const __grid_constant__ CUtensorMap tmap_ws, const TapConvArgs a) {
+  constexpr bool CLUSTER = MODE == MODE_MCAST;     // multicast variant
+  constexpr bool PAIR = MODE == MODE_PAIR;
+  constexpr bool MULTI = MODE != MODE_PLAIN;       // launched as a cluster
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
   constexpr int EPI_BYTES = TMA_EPI ? convepi::staging_bytes(BLOCK_N) + convepi::stat_bytes() : 0;
@@ -101,6 +106,12 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* dbg = a.dbg ? a.dbg + 8 * (long long)blockIdx.x : nullptr;
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    dbg[0] = (long long)gt; dbg[1] = clock64();
+  }
   const int wt = a.OW / a.BW, ht = a.OH / a.BH, nt = (a.N + a.BN - 1) / a.BN;
   const int m_tiles = wt * ht * nt;
   const int n_tiles = (a.Cn + BLOCK_N - 1) / BLOCK_N;
@@ -108,19 +119,20 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const bool want_stats = TMA_EPI && a.stat.partial != nullptr;
   // Work units: a unit is one tile, or (cluster variant) a super-tile of cm x cn tiles handled by one cluster in lockstep.
   // Units are numbered class-major; unit -> (class, M super-tile, N super-tile); this CTA takes tile (rm, rn) of the unit.
-  const int cs = CLUSTER ? a.cm * a.cn : 1;
-  const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
-  const int rm = CLUSTER ? crank / a.cn : 0, rn = CLUSTER ? crank % a.cn : 0;
-  const int sn_tiles = CLUSTER ? n_tiles / a.cn : n_tiles;
-  const int class_units = (CLUSTER ? m_tiles / a.cm : m_tiles) * sn_tiles;
+  const int cs = MULTI ? a.cm * a.cn : 1;
+  const int crank = MULTI ? (int)cluster_rank() : 0;
+  const bool leader = crank == 0;                  // PAIR: the CTA that issues the MMAs
+  const int rm = MULTI ? crank / a.cn : 0, rn = MULTI ? crank % a.cn : 0;
+  const int sn_tiles = MULTI ? n_tiles / a.cn : n_tiles;
+  const int class_units = (MULTI ? m_tiles / a.cm : m_tiles) * sn_tiles;
   const int num_units = class_units * a.nclass;
   const int unit0 = blockIdx.x / cs, unit_step = gridDim.x / cs;
   auto decode = [&](int unit, int& cls, int& mt, int& n0) {
     cls = unit / class_units;
     const int cu = unit - cls * class_units;
     const int smt = cu / sn_tiles, snt = cu - smt * sn_tiles;
-    mt = CLUSTER ? smt * a.cm + rm : smt;
-    n0 = (CLUSTER ? snt * a.cn + rn : snt) * BLOCK_N;
+    mt = MULTI ? smt * a.cm + rm : smt;
+    n0 = (MULTI ? snt * a.cn + rn : snt) * BLOCK_N;
   };
   // multicast masks: the CTAs of my cluster row (they receive my A slice) and of my cluster column (my B slice)
   uint16_t mask_row = 1, mask_col = 1;
@@ -132,17 +144,21 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(CLUSTER ? &tmap_xs : &tmap_x);
-    prefetch_tmap(CLUSTER ? &tmap_ws : &tmap_w);
+    prefetch_tmap(CLUSTER || (PAIR && !B_MN) ? &tmap_ws : &tmap_w);
     if (TMA_EPI) prefetch_tmap(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     // a slot is free again when every CTA that reads what I multicast into it has consumed it: my row and my column
     const int releases = CLUSTER ? a.cm + a.cn - 1 : 1;
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], releases); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], PAIR ? 8 : 4); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_base_slot);
+  if (PAIR) cluster_sync_all();                    // both CTAs' barriers exist before the paired TMEM allocation / any remote signal
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_2sm<TMEM_COLS>(tmem_base_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_base_slot);
+  }
   if (TMA_EPI && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 2 * convepi::STAT_PARTS * convepi::STAT_MAX_C; i += convepi::EPI_THREADS) s_stat[i] = 0.f;
   }
@@ -151,6 +167,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   if (CLUSTER) cluster_sync_all();                 // every barrier of the cluster is initialised before anyone signals a peer
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (dbg && threadIdx.x == 0) dbg[2] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -172,6 +189,21 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
+          if (PAIR) {
+            // ONE arrival (the leader's) carries the bytes of both CTAs; the peer's loads complete on the leader's barrier
+            const uint32_t lead_full = map_to_cta(&full_bar[stage], 0);
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            tma_load_4d_2sm(sa, &tmap_x, c0, w0 * a.in_mul + a.tap_dw[tap], h0 * a.in_mul + a.tap_dh[tap], nb0, lead_full);
+            if (!B_MN) {
+              tma_load_2d_2sm(sb, &tmap_ws, a.tap_wcol[tap] + c0, n0 + crank * (BLOCK_N / 2), lead_full);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 128; ++j)
+                tma_load_2d_2sm(sb + j * (BLOCK_K * 128), &tmap_w, a.tap_wcol[tap] + n0 + crank * (BLOCK_N / 2) + 64 * j, c0, lead_full);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (!CLUSTER) {
             // activation patch of this tap: (strided) 4-D box, out-of-range pixels zero-filled by TMA
@@ -200,10 +232,10 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && (!PAIR || leader)) {
+    // ===================== MMA issuer (PAIR: leader CTA only) =====================
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, false, B_MN);
+      const uint32_t idesc = make_idesc(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, false, B_MN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_step) {
@@ -214,6 +246,7 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (dbg && kb == 0 && unit == unit0) dbg[3] = clock64();
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -222,13 +255,17 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adv_a = (uint64_t)((k * UMMA_K * 2) >> 4);
             const uint64_t adv_b = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-            umma_f16(tmem_d, da + adv_a, db + adv_b, idesc, (kb | k) ? 1u : 0u);
+            if (PAIR) umma_f16_2sm(tmem_d, da + adv_a, db + adv_b, idesc, (kb | k) ? 1u : 0u);
+            else umma_f16(tmem_d, da + adv_a, db + adv_b, idesc, (kb | k) ? 1u : 0u);
           }
-          if (CLUSTER) tcgen05_commit_mc(&empty_bar[stage], mask_row | mask_col);   // release the slot at every CTA that fills it
+          if (PAIR) commit_2sm(&empty_bar[stage]);                                  // both CTAs' producers
+          else if (CLUSTER) tcgen05_commit_mc(&empty_bar[stage], mask_row | mask_col);   // every CTA that fills the slot
           else tcgen05_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tmem_full[acc]);
+        if (PAIR) commit_2sm(&tmem_full[acc]);                                      // both epilogues
+        else tcgen05_commit(&tmem_full[acc]);
+        if (dbg) dbg[4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -247,12 +284,13 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       decode(unit, cls, mt, n0);
       const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (dbg && et == 0) dbg[5] = clock64();
       tcgen05_fence_after();
       if (TMA_EPI) {
         int valid_rows = (a.N - nb0) * a.BW * a.BH;
         if (valid_rows > BLOCK_M) valid_rows = BLOCK_M;
         convepi::drain_tile<BLOCK_N>(tmem_base + (uint32_t)(acc * BLOCK_N), sbuf, s_stat, et, valid_rows, n0, a.Cn, a.bias_f32,
-                                     a.bias_bf16, &tmem_empty[acc]);
+                                     a.bias_bf16, &tmem_empty[acc], PAIR && !leader ? map_to_cta(&tmem_empty[acc], 0) : 0u);
         if (et == 0) {
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
@@ -295,27 +333,41 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (PAIR && !leader) remote_arrive(map_to_cta(&tmem_empty[acc], 0));
+          else mbar_arrive(&tmem_empty[acc]);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (want_stats && stat_keep) sacc.flush(s_stat, et, stat_col0, a.Cn);
     if (TMA_EPI && et == 0) tma_store_wait<0>();                 // every tile of this CTA is in global memory
+    if (dbg && et == 0) dbg[6] = clock64();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (CLUSTER) cluster_sync_all();                 // no CTA leaves while a peer may still multicast into it or signal its barriers
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (MULTI) cluster_sync_all();                   // no CTA leaves while a peer may still write into it or signal its barriers
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    dbg[7] = (long long)gt;                                        // exit (before the statistics ticket / fold, if any)
+  }
   if (want_stats) {
     // one tile per CTA (units <= clusters): slot = M tile, this CTA owns its N-tile's channels; otherwise slot = CTA, all channels
     const bool one_tile = num_units <= unit_step;
     int cls0, mt, n0;
     decode(unit0, cls0, mt, n0);
     const int c_hi = n0 + BLOCK_N < a.Cn ? n0 + BLOCK_N : a.Cn;
+    // one tile per CTA: the CTAs of one channel tile share a ticket and its last CTA folds only that tile's channels (the n_tiles
+    // folds run in parallel); otherwise one ticket for the grid and the last CTA folds every channel
     convepi::finalize_stats<NUM_THREADS>(a.stat, s_stat, convepi::STAT_PARTS, a.Cn, one_tile ? mt : (int)blockIdx.x,
                                          one_tile ? m_tiles : (int)gridDim.x, one_tile ? n0 : 0, one_tile ? c_hi : a.Cn,
-                                         reinterpret_cast<float*>(sbuf));
+                                         reinterpret_cast<float*>(sbuf), one_tile ? n0 / BLOCK_N : 0, one_tile ? m_tiles : -1);
   }
 }
 
@@ -485,15 +537,15 @@ __global__ void wgradg_reduce_kernel(const float* partial, int splits, long long
   *reinterpret_cast<uint2*>(out + i) = o;
 }
 
-template <int BLOCK_N, bool B_MN, bool TMA_EPI, bool CLUSTER>
+template <int BLOCK_N, bool B_MN, bool TMA_EPI, int MODE>
 int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const CUtensorMap& txs, const CUtensorMap& tws,
              const TapConvArgs& a, int grid, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + (MODE == MODE_PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   constexpr int EPI_BYTES = TMA_EPI ? convepi::staging_bytes(BLOCK_N) + convepi::stat_bytes() : 0;
   constexpr int BUDGET = 200 * 1024 - EPI_BYTES;
   constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
-  auto kern = convg_tcgen05_kernel<BLOCK_N, STAGES, B_MN, TMA_EPI, CLUSTER>;
+  auto kern = convg_tcgen05_kernel<BLOCK_N, STAGES, B_MN, TMA_EPI, MODE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -504,20 +556,21 @@ int launch_g(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& to
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CLUSTER ? a.cm * a.cn : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = CLUSTER ? 1 : 0;
+  at[0].val.clusterDim.x = MODE != MODE_PLAIN ? a.cm * a.cn : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = MODE != MODE_PLAIN ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, tout, txs, tws, a);
   return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 template <bool B_MN, bool TMA_EPI>
-int launch_n(int block_n, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const CUtensorMap& txs,
+int launch_n(int block_n, int mode, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, const CUtensorMap& txs,
              const CUtensorMap& tws, const TapConvArgs& a, int grid, cudaStream_t stream) {
-  if (a.cm * a.cn > 1)
-    return block_n == 64 ? launch_g<64, B_MN, TMA_EPI, true>(tx, tw, tout, txs, tws, a, grid, stream)
-                         : launch_g<128, B_MN, TMA_EPI, true>(tx, tw, tout, txs, tws, a, grid, stream);
-  return block_n == 64 ? launch_g<64, B_MN, TMA_EPI, false>(tx, tw, tout, txs, tws, a, grid, stream)
-                       : launch_g<128, B_MN, TMA_EPI, false>(tx, tw, tout, txs, tws, a, grid, stream);
+  if (mode == MODE_PAIR) return launch_g<128, B_MN, TMA_EPI, MODE_PAIR>(tx, tw, tout, txs, tws, a, grid, stream);
+  if (mode == MODE_MCAST)
+    return block_n == 64 ? launch_g<64, B_MN, TMA_EPI, MODE_MCAST>(tx, tw, tout, txs, tws, a, grid, stream)
+                         : launch_g<128, B_MN, TMA_EPI, MODE_MCAST>(tx, tw, tout, txs, tws, a, grid, stream);
+  return block_n == 64 ? launch_g<64, B_MN, TMA_EPI, MODE_PLAIN>(tx, tw, tout, txs, tws, a, grid, stream)
+                       : launch_g<128, B_MN, TMA_EPI, MODE_PLAIN>(tx, tw, tout, txs, tws, a, grid, stream);
 }
 
 // patch shape for an iteration space of OH x OW pixels per image: BW * BH * BN == pixels with BW | OW and BH | OH (the largest
@@ -543,7 +596,8 @@ void patch_shape(int OH, int OW, int pixels, int& BW, int& BH, int& BN) {
 // is cm = cn = 1 with the tile width chosen by the model below; DRACO_CONV_CLUSTER="cm,cn[,block_n]" forces a cluster shape
 // ("auto" lets the model pick one) for experiments and for the tests that keep the multicast path honest.
 // Model: a tile costs k_blocks * (A/cn + B/cm) bytes of L2 -> SM traffic and k_blocks * 4 MMAs of BLOCK_N/2 clocks.
-struct TapPlan { int block_n, cm, cn, grid, units; };
+constexpr bool PAIR_DEFAULT = false;
+struct TapPlan { int block_n, cm, cn, grid, units, mode; };
 
 int clusters_resident(int cs, int num_sms) {
   // GPCs of a B200 expose 16-20 SMs each and a cluster never spans GPCs: count conservatively
@@ -555,14 +609,24 @@ int clusters_resident(int cs, int num_sms) {
 
 TapPlan plan_tap(int m_tiles, int Cn, int k_blocks_total, int nclass, bool b_mn, int num_sms) {
   int f_cm = 1, f_cn = 1, f_bn = Cn >= 128 ? 128 : 64;          // default: no cluster, 128-wide tiles when the layer has them
-  if (const char* e = getenv("DRACO_CONV_CLUSTER")) {
+  const char* e0 = getenv("DRACO_CONV_CLUSTER");
+  bool want_pair = PAIR_DEFAULT;
+  if (e0 && e0[0] == 'p') want_pair = true;                       // "pair"
+  else if (e0) want_pair = false;
+  if (want_pair && Cn % 128 == 0 && m_tiles % 2 == 0) {
+    // CTA pairs (cta_group::2): 256 x 128 tiles, one pair per two SMs
+    const long long units = (long long)(m_tiles / 2) * (Cn / 128) * nclass;
+    const long long pairs = units < num_sms / 2 ? units : num_sms / 2;
+    return {128, 2, 1, (int)(pairs * 2), (int)units, MODE_PAIR};
+  }
+  if (const char* e = (e0 && e0[0] != 'p') ? e0 : nullptr) {
     int x = 0, y = 0, z = 0;
     const int got = sscanf(e, "%d,%d,%d", &x, &y, &z);
     if (got >= 2) { f_cm = x; f_cn = y; f_bn = -1; }
     else if (e[0] == 'a') { f_cm = f_cn = f_bn = -1; }
     if (got >= 3) f_bn = z;
   }
-  TapPlan best = {Cn >= 128 ? 128 : 64, 1, 1, 0, 0};
+  TapPlan best = {Cn >= 128 ? 128 : 64, 1, 1, 0, 0, MODE_PLAIN};
   double best_t = 1e30;
   for (int bn = 128; bn >= 64; bn -= 64) {
     if (bn > Cn && bn != 64) continue;
@@ -586,7 +650,7 @@ TapPlan plan_tap(int m_tiles, int Cn, int k_blocks_total, int nclass, bool b_mn,
         double t = t_mma > t_sm ? t_mma : t_sm;
         if (t_chip > t) t = t_chip;
         t += waves * 600 + (cs > 1 ? 400 : 0);                      // epilogue tail per wave, cluster launch + syncs
-        if (t < best_t) { best_t = t; best = {bn, cm, cn, (int)(clusters * cs), (int)units}; }
+        if (t < best_t) { best_t = t; best = {bn, cm, cn, (int)(clusters * cs), (int)units, cs > 1 ? MODE_MCAST : MODE_PLAIN}; }
       }
     }
   }
@@ -650,7 +714,7 @@ extern "C" int drc_convg_stat_slots(int N, int H, int W, int Cout, int stride, i
   return m_tiles > num_sms ? m_tiles : num_sms;
 }
 
-// Test hook: the plan (block_n, cm, cn, grid) the launcher would use.
+// Test hook: the plan (block_n, cm, cn, grid, mode: 0 plain / 1 multicast cluster / 2 CTA pair) the launcher would use (5 ints).
 extern "C" int drc_convg_plan(int N, int H, int W, int Cin, int Cout, int ks, int stride, int dgrad, int num_sms, int* out4) {
   if (!drc_convg_supported(H, W, Cin, Cout, ks, stride)) return -1;
   const int OH = H / stride, OW = W / stride;
@@ -662,9 +726,13 @@ extern "C" int drc_convg_plan(int N, int H, int W, int Cin, int Cout, int ks, in
   int nclass = 1, ntaps = ks * ks;
   if (strided_dgrad) { nclass = ks == 1 ? 1 : stride * stride; ntaps = ks * ks; }
   const TapPlan p = plan_tap(m_tiles, Cn, ntaps * (Cred / BLOCK_K), nclass, dgrad != 0, num_sms);
-  out4[0] = p.block_n; out4[1] = p.cm; out4[2] = p.cn; out4[3] = p.grid;
+  out4[0] = p.block_n; out4[1] = p.cm; out4[2] = p.cn; out4[3] = p.grid; out4[4] = p.mode;
   return 0;
 }
+
+// Test / profiling hook: the next drc_convg launches write their per-CTA timeline (8 x int64 per CTA) here; null disables.
+static long long* g_convg_dbg = nullptr;
+extern "C" void drc_convg_set_timeline(long long* buf) { g_convg_dbg = buf; }
 
 extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int H, int W, int Cin, int Cout, int ks, int stride,
                          int dgrad, const float* bias_f32, const void* bias_bf16, int tma_store, float* stat_partial,
@@ -728,7 +796,7 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   // ---- plan + tensor maps
   const TapPlan plan = plan_tap(m_tiles, a.Cn, a.ntaps * (a.Cred / BLOCK_K), a.nclass, dgrad != 0, num_sms);
   const int block_n = plan.block_n;
-  a.cm = plan.cm; a.cn = plan.cn;
+  a.cm = plan.cm; a.cn = plan.cn; a.dbg = g_convg_dbg;
   int fw = 1, fh = 1, fn = 1;
   slice_shape(a.BW, a.BH, a.BN, a.cn, fw, fh, fn);
   a.sl_fw = fw; a.sl_fh = fh;
@@ -736,7 +804,8 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   const long long wcols = (long long)ks * ks * Cin;               // weights as a matrix [Cout rows][ks*ks*Cin cols]
   int r = encode_mat(&tw, wgt, Cout, wcols, wcols, dgrad ? BLOCK_K : block_n);
   if (r) return 2000 + r;
-  r = encode_mat(&tws, wgt, Cout, wcols, wcols, (dgrad ? BLOCK_K : block_n) / a.cm);
+  // MODE_MCAST: 1/cm of the weight tile's rows; MODE_PAIR (K-major B only): this CTA's half of the Cout rows
+  r = encode_mat(&tws, wgt, Cout, wcols, wcols, plan.mode == MODE_PAIR ? (dgrad ? BLOCK_K : block_n / 2) : (dgrad ? BLOCK_K : block_n) / a.cm);
   if (r) return 2100 + r;
   const int aC = dgrad ? Cout : Cin, aW = dgrad ? OW : W, aH = dgrad ? OH : H, aS = dgrad ? 1 : stride;
   r = encode_act(&tx, act, aC, aW, aH, N, a.BW, a.BH, a.BN, aS);
@@ -748,10 +817,10 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
     r = encode_act(&tout, out, a.Cn, a.out_W, a.out_H, N, a.BW, a.BH, a.BN, 1);
     if (r) return 3000 + r;
   }
-  if (!dgrad) return tma_epi ? launch_n<false, true>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream)
-                             : launch_n<false, false>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream);
-  return tma_epi ? launch_n<true, true>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream)
-                 : launch_n<true, false>(block_n, tx, tw, tout, txs, tws, a, plan.grid, stream);
+  if (!dgrad) return tma_epi ? launch_n<false, true>(block_n, plan.mode, tx, tw, tout, txs, tws, a, plan.grid, stream)
+                             : launch_n<false, false>(block_n, plan.mode, tx, tw, tout, txs, tws, a, plan.grid, stream);
+  return tma_epi ? launch_n<true, true>(block_n, plan.mode, tx, tw, tout, txs, tws, a, plan.grid, stream)
+                 : launch_n<true, false>(block_n, plan.mode, tx, tw, tout, txs, tws, a, plan.grid, stream);
 }
 
 namespace {

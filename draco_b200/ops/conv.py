@@ -136,7 +136,7 @@ def _stat_args(req, cout: int, slots: int, device):
     req.invstd = torch.empty(cout, dtype=torch.float32, device=device)
     rm = req.running_mean.data_ptr() if req.running_mean is not None else None
     rv = req.running_var.data_ptr() if req.running_var is not None else None
-    return ((partial.data_ptr(), _counter(device)[12:].data_ptr(), req.mean.data_ptr(), req.invstd.data_ptr(), rm, rv, req.eps,
+    return ((partial.data_ptr(), _counter(device)[16:].data_ptr(), req.mean.data_ptr(), req.invstd.data_ptr(), rm, rv, req.eps,
              req.momentum), (partial,))
 
 
@@ -171,9 +171,10 @@ def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, d
 
 
 def convg_plan(n: int, h: int, w: int, cin: int, cout: int, ks: int, stride: int, dgrad: int, num_sms: int = 148):
-    """[block_n, cm, cn, grid] the tap-convolution launcher picks for this layer (host-side planning only; no GPU needed)."""
+    """[block_n, cm, cn, grid, mode] the tap-convolution launcher picks for this layer (mode 0 = one CTA per tile, 1 = multicast
+    cluster, 2 = CTA pair / cta_group::2); host-side planning only, no GPU needed."""
     import ctypes as C
-    out = (C.c_int * 4)()
+    out = (C.c_int * 5)()
     if _lib().drc_convg_plan(n, h, w, cin, cout, ks, stride, int(dgrad), num_sms, out) != 0:
         return None
     return list(out)

@@ -72,7 +72,7 @@ def _counter(device: torch.device) -> torch.Tensor:
     """Grid-barrier / last-CTA counters; one set per (device, stream) so that concurrent streams never share them."""
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     if key not in _counter_cache:
-        _counter_cache[key] = torch.zeros(16, dtype=torch.int32, device=device)   # zero-filled on this very stream
+        _counter_cache[key] = torch.zeros(32, dtype=torch.int32, device=device)   # zero-filled on this very stream
     return _counter_cache[key]
 
 

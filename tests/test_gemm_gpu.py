@@ -202,13 +202,14 @@ def test_convg_tap_table_kernels(n, cin, cout, hw, ks, stride, epi, monkeypatch)
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("cfg", ["2,1,128", "1,2,128", "2,2,128", "4,2,128", "2,4,64", "8,1,64", "1,8,64", "4,1,128", "1,4,64"])
+@pytest.mark.parametrize("cfg", ["pair", "2,1,128", "1,2,128", "2,2,128", "4,2,128", "2,4,64", "8,1,64", "1,8,64", "4,1,128", "1,4,64"])
 @pytest.mark.parametrize("n,cin,cout,hw,ks,stride", [(128, 256, 256, 8, 3, 1), (128, 512, 512, 4, 3, 1), (128, 128, 256, 16, 3, 2),
                                                      (24, 64, 512, 14, 1, 1)])
 def test_convg_cluster_multicast_shapes(n, cin, cout, hw, ks, stride, cfg, monkeypatch):
-    """Thread-block-cluster variant of the tap convolution: every CTA loads 1/cn of the activation tile and 1/cm of the weight tile
-    and TMA-multicasts them to its cluster row / column.  Each forced cluster shape must reproduce the no-cluster kernel (same
-    k order per output element) for fprop (with fused BatchNorm statistics), dense dgrad and the one-launch stride-2 dgrad."""
+    """Cluster variants of the tap convolution.  "pair": two CTAs execute one tcgen05.mma.cta_group::2 of M = 256 (each stages its
+    own activation tile and half of the weight tile).  "cm,cn,bn": every CTA loads 1/cn of the activation tile and 1/cm of the
+    weight tile and TMA-multicasts them to its cluster row / column.  Each forced shape must reproduce the one-CTA-per-tile kernel
+    (same k order per output element) for fprop (with fused BatchNorm statistics), dense dgrad and the one-launch stride-2 dgrad."""
     from draco_b200.ops.conv import BnStatRequest, convg_plan, convg_tcgen05
     dev = torch.device("cuda", 0)
     torch.manual_seed(n + cin + hw)
@@ -222,16 +223,22 @@ def test_convg_cluster_multicast_shapes(n, cin, cout, hw, ks, stride, cfg, monke
     ref = F.conv2d(x.float(), w.float(), None, stride=stride, padding=ks // 2)
     assert _rel_err(y0, ref) < 1.5e-2
     monkeypatch.setenv("DRACO_CONV_CLUSTER", cfg)
-    cm, cn, bn = (int(v) for v in cfg.split(","))
+    def forced(dgrad):
+        plan = convg_plan(n, hw, hw, cin, cout, ks, stride, dgrad)
+        if cfg == "pair":
+            return plan[4] == 2
+        cm, cn, bn = (int(v) for v in cfg.split(","))
+        return plan[:3] == [bn, cm, cn] and plan[4] == 1
+
     ran = 0
-    if convg_plan(n, hw, hw, cin, cout, ks, stride, 0)[:3] == [bn, cm, cn]:
+    if forced(0):
         rb = BnStatRequest(1e-5, 0.1)
         y1 = convg_tcgen05(x, w, (hw, hw), stride, False, None, bn_stats=rb)
         assert torch.equal(y0, y1)
         assert _rel_err(rb.mean, ra.mean) < 1e-5 and _rel_err(rb.invstd, ra.invstd) < 1e-5
         assert torch.equal(convg_tcgen05(x, w, (hw, hw), stride, False, None), y1)
         ran += 1
-    if convg_plan(n, hw, hw, cin, cout, ks, stride, 1)[:3] == [bn, cm, cn]:
+    if forced(1):
         assert torch.equal(convg_tcgen05(dy, w, (hw, hw), stride, True), dx0)
         ran += 1
     if not ran:
