@@ -5,6 +5,8 @@ mkdir -p gpurun_out
 python -m draco_b200.build > gpurun_out/env.log 2>&1
 for s in "$@"; do
   case $s in
+    alltests) timeout -k 10 1500 python -m pytest tests/ -q -m gpu -p no:cacheprovider -x > gpurun_out/t_all.log 2>&1; echo "alltests rc=$?"; tail -n 4 gpurun_out/t_all.log | cut -c1-300 ;;
+    smoke) timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke.log ;;
     recheck) timeout -k 10 600 python -m pytest tests/test_fused_engine_gpu.py -q -m gpu -p no:cacheprovider -k "compress or phase_times or two_processes or dropout or library_op" > gpurun_out/t_recheck.log 2>&1; echo "recheck rc=$?" ;;
     gemmtests) timeout -k 10 600 python -m pytest tests/test_gemm_gpu.py -q -m gpu -p no:cacheprovider -k "gemm or linear" > gpurun_out/t_gemm.log 2>&1; echo "gemmtests rc=$?" ;;
     gemmbench) timeout -k 10 600 python tools/bench_gemm.py --json gpurun_out/gemm_bench.json > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
