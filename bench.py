@@ -275,7 +275,9 @@ def main() -> int:
         except Exception:
             base = None
         out = {
-            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "metric": METRIC if headline else f"{a.network}/{a.dataset} steps/sec, {a.approach}/{a.mode} r={a.group_size} under "
+                                                f"{a.worker_fail} adversaries (not the headline config)",
+            "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": (value / base) if base else None, "dtype": "bf16", "data": "synthetic",
             "impl": a.impl,
