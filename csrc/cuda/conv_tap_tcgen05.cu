@@ -57,7 +57,6 @@ struct TapConvArgs {
   // are bound by exactly that traffic: ~150 MB per convolution against ~6300 B/clk of L2 throughput).
   int cm, cn;
   long long* dbg;              // optional per-CTA timeline (8 x int64, tools/prof_conv_timeline.py): null in production
-  int dbg_skip;                // profiling only (with dbg): 1 = issue no MMAs, 2 = issue no loads (results are garbage)
   int sl_fw, sl_fh;            // the A slice of CTA column rn: split factors of the patch along w and h (n takes the rest)
   __nv_bfloat16* out;          // [N, out_H, out_W, Cn]
   const float* bias_f32;
@@ -190,11 +189,6 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          if (!MULTI && (a.dbg_skip & 2)) {                    // profiling: MMA-only pipeline
-            mbar_arrive(&full_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
           if (PAIR) {
             // ONE arrival (the leader's) carries the bytes of both CTAs; the peer's loads complete on the leader's barrier
             const uint32_t lead_full = map_to_cta(&full_bar[stage], 0);
@@ -250,9 +244,12 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        if (dbg && unit == unit0) {                                 // profiling: when did the first operands land?
+          mbar_wait(&full_bar[stage], phase);
+          dbg[3] = clock64();
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (dbg && kb == 0 && unit == unit0) dbg[3] = clock64();
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -261,7 +258,6 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adv_a = (uint64_t)((k * UMMA_K * 2) >> 4);
             const uint64_t adv_b = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-            if (a.dbg_skip & 1) continue;                      // profiling: load-only pipeline
             if (PAIR) umma_f16_2sm(tmem_d, da + adv_a, db + adv_b, idesc, (kb | k) ? 1u : 0u);
             else umma_f16(tmem_d, da + adv_a, db + adv_b, idesc, (kb | k) ? 1u : 0u);
           }
@@ -739,9 +735,8 @@ extern "C" int drc_convg_plan(int N, int H, int W, int Cin, int Cout, int ks, in
 
 // Test / profiling hook: the next drc_convg launches write their per-CTA timeline (8 x int64 per CTA) here; null disables.
 static long long* g_convg_dbg = nullptr;
-static int g_convg_dbg_skip = 0;
 extern "C" void drc_convg_set_timeline(long long* buf) { g_convg_dbg = buf; }
-extern "C" void drc_convg_set_skip(int flags) { g_convg_dbg_skip = flags; }
+
 
 extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int H, int W, int Cin, int Cout, int ks, int stride,
                          int dgrad, const float* bias_f32, const void* bias_bf16, int tma_store, float* stat_partial,
@@ -805,7 +800,7 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   // ---- plan + tensor maps
   const TapPlan plan = plan_tap(m_tiles, a.Cn, a.ntaps * (a.Cred / BLOCK_K), a.nclass, dgrad != 0, num_sms);
   const int block_n = plan.block_n;
-  a.cm = plan.cm; a.cn = plan.cn; a.dbg = g_convg_dbg; a.dbg_skip = g_convg_dbg ? g_convg_dbg_skip : 0;
+  a.cm = plan.cm; a.cn = plan.cn; a.dbg = g_convg_dbg;
   int fw = 1, fh = 1, fn = 1;
   slice_shape(a.BW, a.BH, a.BN, a.cn, fw, fh, fn);
   a.sl_fw = fw; a.sl_fh = fh;

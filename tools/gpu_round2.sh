@@ -15,6 +15,7 @@ for s in "$@"; do
     clustersweep) timeout -k 10 300 python -m pytest tests/test_gemm_gpu.py -q -m gpu -p no:cacheprovider -x -k "tap or convg or cluster or statistics or block_fusion" > gpurun_out/t_cluster.log 2>&1; echo "cluster tests rc=$?"; tail -n 5 gpurun_out/t_cluster.log
                  timeout -k 10 600 python tools/sweep_conv_cluster.py > gpurun_out/conv_cluster_sweep.log 2>&1; echo "sweep rc=$?"; tail -n 3 gpurun_out/conv_cluster_sweep.log | cut -c1-400 ;;
     convtimeline) timeout -k 10 300 python tools/prof_conv_timeline.py > gpurun_out/conv_timeline.log 2>&1; echo "convtimeline rc=$?"; tail -n 14 gpurun_out/conv_timeline.log | cut -c1-420 ;;
+    convbench) timeout -k 10 600 python tools/bench_conv.py > gpurun_out/conv_bench.log 2>&1; echo "convbench rc=$?" ;;
     bench1) timeout -k 10 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench1.log 2>&1; echo "bench1 rc=$?" ;;
     bench1_flat) timeout -k 10 600 python bench.py --gpus 1 --steps 20 --warmup 5 --impl nccl_flat > gpurun_out/bench1_flat.log 2>&1; echo "bench1_flat rc=$?" ;;
     bench1_ps) CUDA_DEVICE_MAX_CONNECTIONS=32 timeout -k 10 600 python bench.py --gpus 1 --steps 20 --warmup 5 --ps-stream > gpurun_out/bench1_psstream.log 2>&1; echo "bench1_ps rc=$?" ;;

@@ -16,9 +16,6 @@ dev = torch.device("cuda", 0)
 lib = CV._lib()
 lib.drc_convg_set_timeline.argtypes = [C.c_void_p]
 lib.drc_convg_set_timeline.restype = None
-lib.drc_convg_set_skip.argtypes = [C.c_int]
-lib.drc_convg_set_skip.restype = None
-lib.drc_convg_set_skip({"": 0, "mma": 1, "tma": 2}[os.environ.get("CONV_SKIP", "")])     # profiling: drop the MMAs or the loads
 MHZ = 1965.0
 
 
