@@ -46,7 +46,9 @@ struct BnFwdArgs {
 
 struct BnBwdArgs {
   const __nv_bfloat16* dy;        // [M][C]
-  const __nv_bfloat16* y;         // forward output (ReLU mask), null when relu == 0
+  const __nv_bfloat16* y;         // forward output (ReLU mask); null when relu == 0 -- or when the mask is recomputed from x
+  const float* beta;              // relu && !y: mask = (bf16(fma(x, gamma*invstd, beta - mean*gamma*invstd)) > 0), the forward's own
+                                  // arithmetic (layers without a residual input) -- one tensor less to read in both kernels
   const __nv_bfloat16* x;         // [M][C]
   const float* gamma;
   const float* mean;
@@ -75,6 +77,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return v;
+}
+// did the forward's BatchNorm + ReLU output survive?  Same fp32 arithmetic and the same bf16 rounding as bn_apply_kernel.
+__device__ __forceinline__ bool relu_mask(float x, float scale, float shift) {
+  return __bfloat162float(__float2bfloat16_rn(fmaf(x, scale, shift))) > 0.f;
 }
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) {
   uint4 v;
@@ -106,15 +112,15 @@ __device__ __forceinline__ void cta_fold(const float (&acc)[2][BN_VEC], float* p
 
 __device__ __forceinline__ bool last_cta(unsigned int* counter) {
   __shared__ int s_last;
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned int prev = atomicAdd(counter, 1u);
+    // release the CTA's partial (ordered before this thread by the barrier) with the ticket, acquire everybody else's
+    unsigned int prev;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(counter) : "memory");
     s_last = (prev == gridDim.x - 1);
     if (s_last) *counter = 0;
   }
   __syncthreads();
-  if (s_last) __threadfence();
   return s_last != 0;
 }
 
@@ -240,6 +246,9 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_apply_kernel(const BnFwdArgs
         *reinterpret_cast<uint4*>(a.y + off) = pack8(f); })
 }
 
+// MASK: 0 = no ReLU, 1 = ReLU mask from the saved output y, 2 = mask recomputed from x (specialised: the apply kernel has to fit
+// 64 registers for two CTAs per SM)
+template <int MASK>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   const int tpc = a.C / BN_VEC;
   const int rgroups = BN_THREADS / tpc;
@@ -253,11 +262,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdAr
 #pragma unroll
   for (int i = 0; i < BN_VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
   uint4 dv[BN_UNROLL], xv[BN_UNROLL], yv[BN_UNROLL];
-  const bool relu = a.relu != 0;
+  constexpr bool relu_y = MASK == 1, relu_x = MASK == 2;
+  float sc[BN_VEC], sh[BN_VEC];
+#pragma unroll
+  for (int i = 0; i < BN_VEC; ++i) {
+    sc[i] = relu_x ? a.gamma[cv * BN_VEC + i] * istd[i] : 0.f;
+    sh[i] = relu_x ? fmaf(-mean[i], sc[i], a.beta[cv * BN_VEC + i]) : 0.f;
+  }
   BN_ROW_LOOP(
-      { dv[u] = ldg16(a.dy + off); xv[u] = ldg16(a.x + off); if (relu) yv[u] = ldg16(a.y + off); },
+      { dv[u] = ldg16(a.dy + off); xv[u] = ldg16(a.x + off); if (relu_y) yv[u] = ldg16(a.y + off); },
       { float d[BN_VEC]; float xf[BN_VEC]; unpack8(dv[u], d); unpack8(xv[u], xf);
-        if (relu) { float yf[BN_VEC]; unpack8(yv[u], yf); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+        if (relu_y) { float yf[BN_VEC]; unpack8(yv[u], yf); _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+        if (relu_x) { _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) d[i] = relu_mask(xf[i], sc[i], sh[i]) ? d[i] : 0.f; }
         _Pragma("unroll") for (int i = 0; i < BN_VEC; ++i) { acc[0][i] += d[i]; acc[1][i] = fmaf(d[i], (xf[i] - mean[i]) * istd[i], acc[1][i]); } (void)off; })
   cta_fold(acc, a.partial + (long long)blockIdx.x * 2 * a.C, a.C, rgroups, rg, cv);
   if (last_cta(a.counter)) {
@@ -273,40 +289,50 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdAr
   }
 }
 
+template <int MASK>
 __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_apply_kernel(const BnBwdArgs a) {
   const int tpc = a.C / BN_VEC;
   const int rgroups = BN_THREADS / tpc;
   const int cv = threadIdx.x % tpc, rg = threadIdx.x / tpc;
   // dx = gs * (d - m1 - xhat * m2) with xhat = (x - mean) * istd   ==   A * d + B * x + Cc
   float cA[BN_VEC], cB[BN_VEC], cC[BN_VEC];
+  constexpr bool relu_y = MASK == 1, relu_x = MASK == 2;
+  __shared__ __align__(16) float s_sh[BN_THREADS * BN_VEC];           // the forward's shift per channel (mask recomputation), read per row: keeps
+  if (relu_x) {                                        // the kernel inside 64 registers
+    for (int c = threadIdx.x; c < a.C; c += BN_THREADS) s_sh[c] = fmaf(-a.mean[c], a.gamma[c] * a.invstd[c], a.beta[c]);
+    __syncthreads();
+  }
+  const float* sh = s_sh + cv * BN_VEC;
 #pragma unroll
   for (int i = 0; i < BN_VEC; ++i) {
     const int c = cv * BN_VEC + i;
     const float istd = a.invstd[c], gs = a.gamma[c] * istd, m1 = a.sums[c], m2 = a.sums[a.C + c], mean = a.mean[c];
-    cA[i] = gs;
+    cA[i] = gs;                                        // == the forward's scale
     cB[i] = -gs * m2 * istd;
     cC[i] = gs * (m2 * istd * mean - m1);
   }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   long long r1 = r0 + a.rows_per_cta; if (r1 > a.M) r1 = a.M;
   constexpr int BU = 2;                                            // three streams in flight: keep the register count moderate
-  const bool relu = a.relu != 0;
   long long r = r0 + rg;
   for (; r + (long long)(BU - 1) * rgroups < r1; r += (long long)BU * rgroups) {
     uint4 dv[BU], xv[BU], yv[BU];
 #pragma unroll
     for (int u = 0; u < BU; ++u) {
       const long long off = (r + (long long)u * rgroups) * a.C + cv * BN_VEC;
-      dv[u] = ldg16(a.dy + off); xv[u] = ldg16(a.x + off); if (relu) yv[u] = ldg16(a.y + off);
+      dv[u] = ldg16(a.dy + off); xv[u] = ldg16(a.x + off); if (relu_y) yv[u] = ldg16(a.y + off);
     }
 #pragma unroll
     for (int u = 0; u < BU; ++u) {
       const long long off = (r + (long long)u * rgroups) * a.C + cv * BN_VEC;
       float d[BN_VEC], xf[BN_VEC];
       unpack8(dv[u], d); unpack8(xv[u], xf);
-      if (relu) { float yf[BN_VEC]; unpack8(yv[u], yf);
+      if (relu_y) { float yf[BN_VEC]; unpack8(yv[u], yf);
 #pragma unroll
         for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+      if (relu_x) {
+#pragma unroll
+        for (int i = 0; i < BN_VEC; ++i) d[i] = relu_mask(xf[i], cA[i], sh[i]) ? d[i] : 0.f; }
       if (a.dres) *reinterpret_cast<uint4*>(a.dres + off) = pack8(d);
       float o[BN_VEC];
 #pragma unroll
@@ -319,9 +345,12 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_apply_kernel(const BnBwd
     float d[BN_VEC], xf[BN_VEC];
     const uint4 dvv = ldg16(a.dy + off), xvv = ldg16(a.x + off);
     unpack8(dvv, d); unpack8(xvv, xf);
-    if (relu) { float yf[BN_VEC]; const uint4 yvv = ldg16(a.y + off); unpack8(yvv, yf);
+    if (relu_y) { float yf[BN_VEC]; const uint4 yvv = ldg16(a.y + off); unpack8(yvv, yf);
 #pragma unroll
       for (int i = 0; i < BN_VEC; ++i) d[i] = yf[i] > 0.f ? d[i] : 0.f; }
+    if (relu_x) {
+#pragma unroll
+      for (int i = 0; i < BN_VEC; ++i) d[i] = relu_mask(xf[i], cA[i], sh[i]) ? d[i] : 0.f; }
     if (a.dres) *reinterpret_cast<uint4*>(a.dres + off) = pack8(d);
     float o[BN_VEC];
 #pragma unroll
@@ -386,18 +415,25 @@ extern "C" int drc_bn_fwd(const void* x, const void* res, void* y, const float* 
   return (int)cudaGetLastError();
 }
 
-extern "C" int drc_bn_bwd(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* invstd,
+extern "C" int drc_bn_bwd(const void* dy, const void* y, const void* x, const float* gamma, const float* beta, const float* mean,
+                          const float* invstd,
                           void* dx, void* dres, float* dgamma, float* dbeta, float* partial, float* sums, unsigned int* counter,
                           long long M, int C, int relu, int num_sms, cudaStream_t stream) {
   if (!supported(C)) return -1;
   BnBwdArgs a;
-  a.dy = (const __nv_bfloat16*)dy; a.y = (const __nv_bfloat16*)y; a.x = (const __nv_bfloat16*)x; a.gamma = gamma; a.mean = mean;
-  a.invstd = invstd; a.dx = (__nv_bfloat16*)dx; a.dres = (__nv_bfloat16*)dres; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.dy = (const __nv_bfloat16*)dy; a.y = (const __nv_bfloat16*)y; a.x = (const __nv_bfloat16*)x; a.gamma = gamma; a.beta = beta;
+  a.mean = mean; a.invstd = invstd;
+  if (relu && !y && !beta) return -2; a.dx = (__nv_bfloat16*)dx; a.dres = (__nv_bfloat16*)dres; a.dgamma = dgamma; a.dbeta = dbeta;
   a.partial = partial; a.sums = sums; a.counter = counter; a.M = M; a.C = C; a.relu = relu;
   int grid;
   a.rows_per_cta = plan_rows(M, C, num_sms, true, &grid);
-  bn_bwd_reduce_kernel<<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
+  const int mask = !relu ? 0 : (y ? 1 : 2);
+  if (mask == 0) bn_bwd_reduce_kernel<0><<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
+  else if (mask == 1) bn_bwd_reduce_kernel<1><<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
+  else bn_bwd_reduce_kernel<2><<<grid, BN_THREADS, smem_bytes(C), stream>>>(a);
   a.rows_per_cta = plan_rows(M, C, num_sms, false, &grid);
-  bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
+  if (mask == 0) bn_bwd_apply_kernel<0><<<grid, BN_THREADS, 0, stream>>>(a);
+  else if (mask == 1) bn_bwd_apply_kernel<1><<<grid, BN_THREADS, 0, stream>>>(a);
+  else bn_bwd_apply_kernel<2><<<grid, BN_THREADS, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }

@@ -46,7 +46,9 @@ __host__ __device__ constexpr int stat_bytes() { return 4 * 2 * STAT_MAX_C * 4; 
 template <int BLOCK_N>
 __device__ __forceinline__ void drain_tile(uint32_t tmem_acc, uint8_t* sbuf, float* s_stat, int et, int valid_rows, int col0, int Cn,
                                            const float* bias_f32, const __nv_bfloat16* bias_bf16, uint64_t* tmem_empty_bar,
-                                           uint32_t remote_empty_bar = 0) {
+                                           uint32_t remote_empty_bar = 0, const __nv_bfloat16* resid_row = nullptr) {
+  // resid_row: channel 0 of THIS thread's output pixel in a tensor of the output's shape that is added to the tile before rounding
+  // (dgrad: the gradient arriving over the other branch of a fork, e.g. the residual shortcut); null = nothing to add / row invalid
   const int q = et >> 5, lane = et & 31;
   // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
   if (et == 0) tc::tma_store_wait_read<0>();
@@ -63,6 +65,18 @@ __device__ __forceinline__ void drain_tile(uint32_t tmem_acc, uint8_t* sbuf, flo
       for (int j = 0; j < 32; ++j) {
         const int cc = col0 + c + j;
         if (cc < Cn) f[j] += bias_f32 ? bias_f32[cc] : __bfloat162float(bias_bf16[cc]);
+      }
+    }
+    if (resid_row) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int cc = col0 + c + jj * 8;
+        if (cc < Cn) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(resid_row + cc));
+          const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 g = __bfloat1622float2(rp[e]); f[jj * 8 + 2 * e] += g.x; f[jj * 8 + 2 * e + 1] += g.y; }
+        }
       }
     }
     uint8_t* row = sbuf + (c >> 6) * (128 * 128) + et * 128;

@@ -41,6 +41,7 @@ constexpr int SMEM_BYTES = W_BYTES + STAGES * PATCH_STRIDE + EPI_BYTES + 1024 + 
 
 struct HaloArgs {
   int N, H, W;
+  const __nv_bfloat16* resid;     // optional [N,H,W,64] tensor added to the output in the epilogue (dgrad: the other branch's gradient)
   const float* bias_f32;
   const __nv_bfloat16* bias_bf16;
   convepi::BnStatArgs stat;
@@ -149,8 +150,10 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       const int w0 = (tile % wt) * TW, h0 = ((tile / wt) % ht) * TH, n0 = tile / (wt * ht);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
+      const __nv_bfloat16* rrow = a.resid
+          ? a.resid + (((long long)n0 * a.H + (h0 + et / TW)) * a.W + (w0 + et % TW)) * BLOCK_N : nullptr;
       convepi::drain_tile<BLOCK_N>(tmem_base + (uint32_t)(acc * BLOCK_N), sbuf, s_stat, et, BLOCK_M, 0, BLOCK_N, a.bias_f32, a.bias_bf16,
-                                   &tmem_empty[acc]);
+                                   &tmem_empty[acc], 0u, rrow);
       if (et == 0) {
         tma_store_4d(&tmap_out, sbuf, 0, w0, h0, n0);
         tma_store_commit();
@@ -342,7 +345,7 @@ extern "C" int drc_conv_halo_stat_slots(int N, int H, int W, int num_sms) {
 // act: [N,H,W,64] bf16 (x for fprop, dy for dgrad); wgt: [64,3,3,64] bf16 (arena layout); out: [N,H,W,64] bf16.
 // stat_*: optional fused BatchNorm statistics of the output (fprop only), see drc_convg.
 extern "C" int drc_conv_halo(const void* act, const void* wgt, void* out, int N, int H, int W, int dgrad, const float* bias_f32,
-                             const void* bias_bf16, float* stat_partial, unsigned int* stat_counter, float* stat_mean,
+                             const void* bias_bf16, const void* resid, float* stat_partial, unsigned int* stat_counter, float* stat_mean,
                              float* stat_invstd, float* running_mean, float* running_var, float eps, float momentum, int num_sms,
                              int device, cudaStream_t stream) {
   if (!drc_conv_halo_supported(H, W, 64, 64)) return -1;
@@ -352,6 +355,7 @@ extern "C" int drc_conv_halo(const void* act, const void* wgt, void* out, int N,
   if (!enc) return -2;
   HaloArgs a;
   a.N = N; a.H = H; a.W = W; a.bias_f32 = bias_f32; a.bias_bf16 = (const __nv_bfloat16*)bias_bf16;
+  a.resid = (const __nv_bfloat16*)resid;
   a.stat.partial = stat_partial; a.stat.counter = stat_counter; a.stat.mean = stat_mean; a.stat.invstd = stat_invstd;
   a.stat.running_mean = running_mean; a.stat.running_var = running_var; a.stat.count = (long long)N * H * W;
   a.stat.eps = eps; a.stat.momentum = momentum;

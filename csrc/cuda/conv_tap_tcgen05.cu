@@ -59,6 +59,8 @@ struct TapConvArgs {
   long long* dbg;              // optional per-CTA timeline (8 x int64, tools/prof_conv_timeline.py): null in production
   int sl_fw, sl_fh;            // the A slice of CTA column rn: split factors of the patch along w and h (n takes the rest)
   __nv_bfloat16* out;          // [N, out_H, out_W, Cn]
+  const __nv_bfloat16* resid;  // optional tensor of the output's shape added in the epilogue (dgrad: the gradient of the other
+                               // branch of a fork -- the residual shortcut -- so that autograd's separate add kernel disappears)
   const float* bias_f32;
   const __nv_bfloat16* bias_bf16;
   convepi::BnStatArgs stat;    // BatchNorm statistics of the output (TMA-store epilogue only)
@@ -292,8 +294,13 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       if (TMA_EPI) {
         int valid_rows = (a.N - nb0) * a.BW * a.BH;
         if (valid_rows > BLOCK_M) valid_rows = BLOCK_M;
+        const __nv_bfloat16* rrow = nullptr;
+        if (a.resid && et < valid_rows) {
+          const int rw = w0 + et % a.BW, rh = h0 + (et / a.BW) % a.BH, rn_ = nb0 + et / (a.BW * a.BH);
+          rrow = a.resid + (((long long)rn_ * a.out_H + rh) * a.out_W + rw) * a.Cn;
+        }
         convepi::drain_tile<BLOCK_N>(tmem_base + (uint32_t)(acc * BLOCK_N), sbuf, s_stat, et, valid_rows, n0, a.Cn, a.bias_f32,
-                                     a.bias_bf16, &tmem_empty[acc], PAIR && !leader ? map_to_cta(&tmem_empty[acc], 0) : 0u);
+                                     a.bias_bf16, &tmem_empty[acc], PAIR && !leader ? map_to_cta(&tmem_empty[acc], 0) : 0u, rrow);
         if (et == 0) {
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
@@ -325,6 +332,21 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 if (col0 + j < a.Cn) f[j] += a.bias_f32 ? a.bias_f32[col0 + j] : __bfloat162float(a.bias_bf16[col0 + j]);
             }
             __nv_bfloat16* dst = orow + col0;
+            if (a.resid) {
+              const __nv_bfloat16* rsrc = a.resid + (dst - a.out);
+              if (col0 + 32 <= a.Cn) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rsrc + j));
+                  const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) { const float2 g = __bfloat1622float2(rp[e]); f[j + 2 * e] += g.x; f[j + 2 * e + 1] += g.y; }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (col0 + j < a.Cn) f[j] += __bfloat162float(rsrc[j]);
+              }
+            }
             if (col0 + 32 <= a.Cn) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(f + j);
@@ -733,13 +755,15 @@ extern "C" int drc_convg_plan(int N, int H, int W, int Cin, int Cout, int ks, in
   return 0;
 }
 
+static inline bool dense_out_of(int dgrad, int stride) { return !(dgrad && stride > 1); }
+
 // Test / profiling hook: the next drc_convg launches write their per-CTA timeline (8 x int64 per CTA) here; null disables.
 static long long* g_convg_dbg = nullptr;
 extern "C" void drc_convg_set_timeline(long long* buf) { g_convg_dbg = buf; }
 
 
 extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int H, int W, int Cin, int Cout, int ks, int stride,
-                         int dgrad, const float* bias_f32, const void* bias_bf16, int tma_store, float* stat_partial,
+                         int dgrad, const float* bias_f32, const void* bias_bf16, const void* resid, int tma_store, float* stat_partial,
                          unsigned int* stat_counter, float* stat_mean, float* stat_invstd, float* running_mean, float* running_var,
                          float eps, float momentum, int num_sms, int device, cudaStream_t stream) {
   if (!drc_convg_supported(H, W, Cin, Cout, ks, stride)) return -1;
@@ -750,6 +774,8 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   a.Cred = dgrad ? Cout : Cin; a.Cn = dgrad ? Cin : Cout;
   patch_shape(OH, OW, BLOCK_M, a.BW, a.BH, a.BN);
   a.out = (__nv_bfloat16*)out; a.bias_f32 = bias_f32; a.bias_bf16 = (const __nv_bfloat16*)bias_bf16;
+  a.resid = (const __nv_bfloat16*)resid;
+  if (resid && !dense_out_of(dgrad, stride) && ks == 1) return -6;      // 1x1 / stride 2 dgrad leaves pixels to the memset
   a.stat.partial = nullptr; a.stat.counter = stat_counter; a.stat.mean = stat_mean; a.stat.invstd = stat_invstd;
   a.stat.running_mean = running_mean; a.stat.running_var = running_var; a.stat.count = (long long)N * OH * OW;
   a.stat.eps = eps; a.stat.momentum = momentum;

@@ -53,9 +53,12 @@ class BasicBlock(nn.Module):
                                           FusedBatchNorm2d(planes * self.expansion))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = self.bn1(self.conv1(x, bn=self.bn1), relu=True)      # conv epilogue delivers bn1's batch statistics
+        # conv epilogue delivers bn1's batch statistics; xs is x for the shortcut branch -- its gradient is added to conv1's input
+        # gradient inside conv1's dgrad epilogue (ops/conv.py) instead of by a separate elementwise kernel
+        c1, xs = self.conv1(x, bn=self.bn1, fork=True)
+        out = self.bn1(c1, relu=True)
         # bn2 + shortcut add + relu in one pass (ops/norm.py)
-        return self.bn2(self.conv2(out, bn=self.bn2), residual=_shortcut(self.shortcut, x), relu=True)
+        return self.bn2(self.conv2(out, bn=self.bn2), residual=_shortcut(self.shortcut, xs), relu=True)
 
 
 class Bottleneck(nn.Module):

@@ -85,7 +85,7 @@ def _lib():
         lib.drc_convg_stat_slots.restype = C.c_int
         lib.drc_convg_plan.argtypes = [C.c_int] * 9 + [C.POINTER(C.c_int)]
         lib.drc_convg_plan.restype = C.c_int
-        lib.drc_convg.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 8 + [N.ptr, N.ptr, C.c_int] + [N.ptr] * 6
+        lib.drc_convg.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 8 + [N.ptr, N.ptr, N.ptr, C.c_int] + [N.ptr] * 6
                                   + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
         lib.drc_convg.restype = C.c_int
         lib.drc_convg_wgrad_supported.argtypes = [C.c_int] * 6
@@ -98,7 +98,7 @@ def _lib():
         lib.drc_conv_halo_supported.restype = C.c_int
         lib.drc_conv_halo_stat_slots.argtypes = [C.c_int] * 4
         lib.drc_conv_halo_stat_slots.restype = C.c_int
-        lib.drc_conv_halo.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr] + [N.ptr] * 6
+        lib.drc_conv_halo.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr, N.ptr] + [N.ptr] * 6
                                       + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
         lib.drc_conv_halo.restype = C.c_int
         lib.drc_conv_halo_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 5 + [N.ptr]
@@ -144,9 +144,10 @@ def _stat_args(req, cout: int, slots: int, device):
 # tap-table implicit-GEMM kernels (csrc/cuda/conv_tap_tcgen05.cu): stride 1 or 2, 1x1 or 3x3, fprop / dgrad / split-K wgrad
 # ---------------------------------------------------------------------------------------------------------------------
 def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, dgrad: bool = False,
-                  bias: torch.Tensor = None, bn_stats: "BnStatRequest" = None) -> torch.Tensor:
+                  bias: torch.Tensor = None, bn_stats: "BnStatRequest" = None, residual: torch.Tensor = None) -> torch.Tensor:
     """``dgrad=False``: ``act`` = x [N, Cin, H, W] -> y [N, Cout, H/stride, W/stride];  ``dgrad=True``: ``act`` = dy -> dx.
-    ``in_hw`` is the spatial size of the forward input x; ``weight`` [Cout, Cin, ks, ks] in channels-last storage."""
+    ``in_hw`` is the spatial size of the forward input x; ``weight`` [Cout, Cin, ks, ks] in channels-last storage.
+    ``residual``: channels-last bf16 tensor of the output's shape added in the epilogue (not for the 1x1 / stride-2 dgrad)."""
     from .. import _native as N
     from . import kernels as K
     lib = _lib()
@@ -162,10 +163,13 @@ def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, d
     sms = K.sm_count(act.device)
     tma = 0 if os.environ.get("DRACO_CONV_EPI", "tma") == "direct" else 1
     assert bn_stats is None or (tma and not dgrad)
+    assert residual is None or (residual.shape == out.shape and residual.dtype == torch.bfloat16
+                                and residual.is_contiguous(memory_format=torch.channels_last))
     slots = lib.drc_convg_stat_slots(n, h, w, cout, stride, sms) if bn_stats is not None else 0
     st, keep = _stat_args(bn_stats, cout, slots, act.device)
     N.check(lib.drc_convg(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, cin, cout, ks, stride, int(dgrad), bf32, bb16,
-                          tma, *st, sms, act.device.index, torch.cuda.current_stream().cuda_stream), "convg")
+                          residual.data_ptr() if residual is not None else None, tma, *st, sms, act.device.index,
+                          torch.cuda.current_stream().cuda_stream), "convg")
     del keep
     return out
 
@@ -205,7 +209,7 @@ def halo_supported(h: int, w: int, cin: int, cout: int) -> bool:
 
 
 def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None,
-                 bn_stats: "BnStatRequest" = None) -> torch.Tensor:
+                 bn_stats: "BnStatRequest" = None, residual: torch.Tensor = None) -> torch.Tensor:
     from .. import _native as N
     from . import kernels as K
     lib = _lib()
@@ -217,7 +221,10 @@ def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, b
     sms = K.sm_count(act.device)
     slots = lib.drc_conv_halo_stat_slots(n, h, w, sms) if bn_stats is not None else 0
     st, keep = _stat_args(bn_stats, 64, slots, act.device)
-    N.check(lib.drc_conv_halo(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, int(dgrad), bf32, bb16, *st, sms,
+    assert residual is None or (residual.shape == out.shape and residual.dtype == torch.bfloat16
+                                and residual.is_contiguous(memory_format=torch.channels_last))
+    N.check(lib.drc_conv_halo(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, int(dgrad), bf32, bb16,
+                              residual.data_ptr() if residual is not None else None, *st, sms,
                               act.device.index, torch.cuda.current_stream().cuda_stream), "conv_halo")
     del keep
     return out
@@ -300,11 +307,13 @@ class _ConvStemFn(torch.autograd.Function):
 
 
 class _ConvGFn(torch.autograd.Function):
-    """3x3 / 1x1, stride 1 / 2 convolution on the tcgen05 kernels.  Returns (y, mean, invstd); the last two are the fused
-    BatchNorm statistics when ``bn_req`` is given (empty tensors otherwise) and carry no gradient."""
+    """3x3 / 1x1, stride 1 / 2 convolution on the tcgen05 kernels.  Returns (y, mean, invstd, x_fork); mean / invstd are the
+    fused BatchNorm statistics when ``bn_req`` is given (empty tensors otherwise) and carry no gradient.  ``x_fork`` (``fork=True``)
+    is x again, for the OTHER consumer of x (the residual shortcut): its gradient comes back into this function and is added to dx
+    inside the dgrad kernel's epilogue instead of by a separate elementwise kernel of autograd."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, bn_req):
+    def forward(ctx, x, weight, bias, stride, bn_req, fork=False):
         ctx.save_for_backward(x, weight)
         ctx.stride, ctx.has_bias = stride, bias is not None
         ctx.set_materialize_grads(False)          # no zero-filled "gradients" for the statistics outputs
@@ -320,13 +329,20 @@ class _ConvGFn(torch.autograd.Function):
         else:
             mean, invstd = x.new_empty(0, dtype=torch.float32), x.new_empty(0, dtype=torch.float32)
         ctx.mark_non_differentiable(mean, invstd)
-        return y, mean, invstd
+        return y, mean, invstd, (x.view_as(x) if fork else x.new_empty(0))
 
     @staticmethod
-    def backward(ctx, dy, _dmean, _dinvstd):
+    def backward(ctx, dy, _dmean, _dinvstd, dfork):
         x, weight = ctx.saved_tensors
+        if dy is None:                                # only the fork branch carried a gradient
+            return dfork, None, None, None, None, None
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
+        if dfork is not None and dfork.numel() == 0:
+            dfork = None
+        if dfork is not None and not (dfork.dtype == torch.bfloat16 and dfork.is_contiguous(memory_format=torch.channels_last)):
+            dfork = dfork.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        fuse_fork = dfork is not None and ctx.needs_input_grad[0] and not (weight.shape[2] == 1 and ctx.stride > 1)
         dx = dw = db = None
         backend_counters["tcgen05"] += 1
         def wgrad():
@@ -345,15 +361,18 @@ class _ConvGFn(torch.autograd.Function):
                 dy.record_stream(side)             # ... and the other way round for its inputs
                 x.record_stream(side)
         if ctx.needs_input_grad[0]:
+            res = dfork if fuse_fork else None
             if ctx.halo:
-                dx = conv3x3_halo(dy, weight, True)
+                dx = conv3x3_halo(dy, weight, True, None, None, res)
             else:
-                dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True)
+                dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True, None, None, res)
+            if dfork is not None and not fuse_fork:
+                dx = dx + dfork
         if ctx.needs_input_grad[1] and dw is None:
             dw = wgrad()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum((0, 2, 3))
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class Conv2d(nn.Conv2d):
@@ -392,7 +411,18 @@ class Conv2d(nn.Conv2d):
                 and self.weight.permute(0, 2, 3, 1).is_contiguous()
                 and bool(_lib().drc_conv_stem_supported(x.shape[2], x.shape[3], 3, 64)))
 
-    def forward(self, x: torch.Tensor, bn: nn.Module = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, bn: nn.Module = None, fork: bool = False):
+        """``fork=True`` returns ``(y, x_fork)``: ``x_fork`` is x for the second consumer of x (the shortcut branch of a residual
+        block); on the tcgen05 path the gradient that comes back through it is added inside this layer's dgrad epilogue."""
+        if fork:
+            if self._tap_ok(x) and x.requires_grad and os.environ.get("DRACO_CONV_FORK", "1") != "0":
+                backend_counters["tcgen05"] += 1
+                req = bn.stat_request(x, self.out_channels) if (bn is not None and hasattr(bn, "stat_request")) else None
+                y, mean, invstd, xf = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req, True)
+                if req is not None:
+                    bn.pending_stats = (y, mean, invstd)
+                return y, xf
+            return self.forward(x, bn=bn), x
         if self._stem_ok(x):
             backend_counters["native_stem"] = backend_counters.get("native_stem", 0) + 1
             req = bn.stat_request(x, self.out_channels) if (bn is not None and hasattr(bn, "stat_request")) else None
@@ -403,7 +433,7 @@ class Conv2d(nn.Conv2d):
         if self._tap_ok(x):
             backend_counters["tcgen05"] += 1
             req = bn.stat_request(x, self.out_channels) if (bn is not None and hasattr(bn, "stat_request")) else None
-            y, mean, invstd = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req)
+            y, mean, invstd, _ = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req)
             if req is not None:
                 bn.pending_stats = (y, mean, invstd)
             return y

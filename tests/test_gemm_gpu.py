@@ -202,6 +202,39 @@ def test_convg_tap_table_kernels(n, cin, cout, hw, ks, stride, epi, monkeypatch)
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("n,cin,cout,hw,ks,stride", [(128, 64, 64, 32, 3, 1), (16, 128, 128, 16, 3, 1), (128, 64, 128, 32, 3, 2),
+                                                     (5, 256, 512, 8, 3, 2), (7, 512, 64, 2, 3, 1), (6, 64, 64, 56, 3, 1)])
+def test_conv_dgrad_epilogue_adds_fork_gradient(n, cin, cout, hw, ks, stride):
+    """dgrad with a residual tensor added in the epilogue (halo kernel, dense tap kernel, one-launch stride-2 tap kernel): equals
+    the plain dgrad plus the tensor in fp32, rounded once; and through autograd a forked input (residual block) gets the same
+    gradient as conv + identity shortcut in fp32."""
+    from draco_b200.ops.conv import Conv2d, conv3x3_halo, convg_tcgen05, halo_supported
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(n + cin + hw + stride)
+    w = _wt(cout, cin, ks, dev)
+    dy = _cl(torch.randn(n, cout, hw // stride, hw // stride, device=dev))
+    r = _cl(torch.randn(n, cin, hw, hw, device=dev))
+    ref = torch.nn.grad.conv2d_input((n, cin, hw, hw), w.float(), dy.float(), stride=stride, padding=ks // 2) + r.float()
+    dx = convg_tcgen05(dy, w, (hw, hw), stride, True, None, None, r)
+    assert _rel_err(dx, ref) < 1.5e-2, _rel_err(dx, ref)
+    assert torch.equal(dx, convg_tcgen05(dy, w, (hw, hw), stride, True, None, None, r))
+    if stride == 1 and halo_supported(hw, hw, cin, cout):
+        dxh = conv3x3_halo(dy, w, True, None, None, r)
+        assert _rel_err(dxh, ref) < 1.5e-2, _rel_err(dxh, ref)
+    # autograd: y = conv(x) ; z = y.sum-like + fork
+    conv = Conv2d(cin, cout, kernel_size=ks, stride=stride, padding=ks // 2, bias=False).to(dev).to(torch.bfloat16)
+    conv.weight.data = w.clone()
+    x = _cl(torch.randn(n, cin, hw, hw, device=dev)).requires_grad_(True)
+    y, xf = conv(x, fork=True)
+    gz = _cl(torch.randn_like(y))
+    (y.float() * gz.float()).sum().add((xf.float() * r.float()).sum()).backward()
+    x32 = x.detach().float().requires_grad_(True)
+    y32 = F.conv2d(x32, w.float(), stride=stride, padding=ks // 2)
+    ((y32 * gz.float()).sum() + (x32 * r.float()).sum()).backward()
+    assert _rel_err(x.grad, x32.grad) < 2e-2, _rel_err(x.grad, x32.grad)
+
+
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("cfg", ["pair", "2,1,128", "1,2,128", "2,2,128", "4,2,128", "2,4,64", "8,1,64", "1,8,64", "4,1,128", "1,4,64"])
 @pytest.mark.parametrize("n,cin,cout,hw,ks,stride", [(128, 256, 256, 8, 3, 1), (128, 512, 512, 4, 3, 1), (128, 128, 256, 16, 3, 2),
                                                      (24, 64, 512, 14, 1, 1)])

@@ -148,3 +148,27 @@ def test_fused_bn_is_deterministic(shape):
         outs.append((y.detach(), xi.grad, bn.weight.grad, bn.bias.grad, bn.running_var.clone()))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("shape", [(128, 64, 32, 32), (16, 256, 8, 8), (2, 2048, 4, 4), (3, 8, 5, 7)])
+def test_fused_bn_relu_mask_recomputed_from_x_is_bit_identical(shape, monkeypatch):
+    """DRACO_BN_MASK=x: backward recomputes the ReLU mask from x with the forward's own arithmetic instead of reading the saved
+    output (one saved activation less).  Same mask, so the gradients are bit-identical to the default path."""
+    from draco_b200.ops.norm import FusedBatchNorm2d
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(sum(shape))
+    x = (torch.randn(shape, device=dev) * 1.7 + 0.3).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(shape, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    grads = {}
+    for mode in ("y", "x"):
+        monkeypatch.setenv("DRACO_BN_MASK", mode)
+        bn = FusedBatchNorm2d(shape[1]).to(dev)
+        with torch.no_grad():
+            bn.weight.copy_(torch.linspace(0.5, 1.5, shape[1]))
+            bn.bias.copy_(torch.linspace(-0.5, 0.5, shape[1]))
+        xg = x.clone().requires_grad_(True)
+        y = bn(xg, relu=True)
+        y.backward(gy)
+        grads[mode] = (y.detach().clone(), xg.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone())
+    for a, b in zip(grads["y"], grads["x"]):
+        assert torch.equal(a, b)

@@ -122,7 +122,7 @@ for (c, hw) in [(64, 32), (128, 16), (256, 8), (512, 4)]:
         return NM._BnActFn.backward(ctx_stub, gy)
 
     class _Ctx:
-        saved_tensors = (x, sy, bn.weight, mean, invstd)
+        saved_tensors = (x, None, bn.weight, bn.bias, mean, invstd)
         relu, has_res = True, False
     ctx_stub = _Ctx()
 

@@ -17,9 +17,13 @@ net = sys.argv[1] if len(sys.argv) > 1 else "ResNet18"
 out_dir = "gpurun_out"
 os.makedirs(out_dir, exist_ok=True)
 from draco_b200.ops import conv as _C  # noqa: E402
-for mode in ("fused", "fused_wgrad_stream", "aten"):
+MODES = os.environ.get("WORKER_MODES", "fused,fused_wgrad_stream,aten").split(",")
+for mode in MODES:
+    # fused[_wgrad_stream][_nofork][_maskx]: A/B switches of single optimisations, same process, same box
     os.environ["DRACO_BN"] = "aten" if mode == "aten" else "fused"
-    _C.WGRAD_SIDE_STREAM = mode == "fused_wgrad_stream"
+    os.environ["DRACO_CONV_FORK"] = "0" if "nofork" in mode else "1"
+    os.environ["DRACO_BN_MASK"] = "x" if "maskx" in mode else "y"
+    _C.WGRAD_SIDE_STREAM = "wgrad_stream" in mode
     cfg = JobConfig(network=net, dataset="Cifar10", approach="baseline", mode="normal", batch_size=128, num_workers=1,
                     dtype="bf16", synthetic_size=1024, transport="nvl").resolve(1)
     ds = synthetic_dataset("Cifar10", 1024)
