@@ -26,49 +26,95 @@ __device__ __forceinline__ int pair_bit(int i, int j) {   // i < j < 8  -> 0..27
   return j * (j - 1) / 2 + i;
 }
 
+// Pair mismatches of one group for this thread's float4 (members v[0..r)).
+__device__ __forceinline__ unsigned int pair_mask(const float4* v, int r) {
+  unsigned int m = 0u;
+#pragma unroll
+  for (int j = 1; j < DRC_MAX_R; ++j) {
+#pragma unroll
+    for (int i = 0; i < j; ++i) {
+      if (j < r) {
+        bool ne = (v[i].x != v[j].x) | (v[i].y != v[j].y) | (v[i].z != v[j].z) | (v[i].w != v[j].w);
+        m |= ne ? (1u << pair_bit(i, j)) : 0u;
+      }
+    }
+  }
+  return m;
+}
+
+// FAST: G <= 4 groups of <= 4 members (the 7-worker / r=3 job: groups of 3 and 4).  Every member load of a tile -- all groups --
+// is issued before the first compare, so a thread keeps G * r independent 16-byte loads in flight instead of r (the kernel is a
+// pure stream over P gradient slabs: memory-level parallelism is the only thing that matters).
+template <bool FAST>
 __global__ void __launch_bounds__(DRC_THREADS) vote_compare_kernel(const __grid_constant__ VoteArgs a) {
-  __shared__ unsigned int s_mask[DRC_MAX_WORKERS];       // one word per group (G <= 32)
+  __shared__ int s_slot[DRC_MAX_WORKERS * DRC_MAX_R];
+  for (int i = threadIdx.x; i < a.G * a.max_r; i += DRC_THREADS) s_slot[i] = a.group_table[i];
+  __syncthreads();
   const int tile_end = a.tile_end > 0 ? a.tile_end : a.tv.ntiles;
+  // Per-thread mismatch masks live in registers across the CTA's tiles and are flushed (warp OR + one global atomic per warp,
+  // only when something differed) when the tensor changes: no barrier and no shared memory in the streaming loop, so the loads
+  // of consecutive tiles overlap.
+  constexpr int NG = FAST ? 4 : DRC_MAX_WORKERS;
+  unsigned int acc[FAST ? 4 : 1];
+#pragma unroll
+  for (int g = 0; g < (FAST ? 4 : 1); ++g) acc[g] = 0u;
+  int cur_tensor = -1;
+  auto flush = [&](int tensor) {
+    if (!FAST || tensor < 0) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < a.G) {
+        const unsigned int m = __reduce_or_sync(0xffffffffu, acc[g]);
+        if ((threadIdx.x & 31) == 0 && m) atomicOr(&a.neq_mask[g * a.tv.ntensors + tensor], m);
+        acc[g] = 0u;
+      }
+    }
+  };
+  (void)NG;
   for (int tile = a.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     int tensor;
     const int valid = tile_valid(a.tv, tile, tensor);
-    if (threadIdx.x < a.G) s_mask[threadIdx.x] = 0u;
-    __syncthreads();
     const long long idx = (long long)tile * DRC_TILE + threadIdx.x * 4;
     const bool active = (int)threadIdx.x * 4 < valid;     // padding is zero in every slot: skip whole float4s only
-    for (int g = 0; g < a.G; ++g) {
-      float4 v[DRC_MAX_R];
-      int r = 0;
+    if (FAST) {
+      if (tensor != cur_tensor) { flush(cur_tensor); cur_tensor = tensor; }
+      float4 v[4][4];
 #pragma unroll
-      for (int k = 0; k < DRC_MAX_R; ++k) {
-        int slot = k < a.max_r ? a.group_table[g * a.max_r + k] : -1;
-        if (slot >= 0) {
-          r = k + 1;
-          if (active) v[k] = ld_f4(reinterpret_cast<const float4*>(a.grad_in + slot * a.slot_stride + idx));
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int slot = (g < a.G && k < a.max_r) ? s_slot[g * a.max_r + k] : -1;
+          if (slot >= 0 && active) v[g][k] = ld_f4(reinterpret_cast<const float4*>(a.grad_in + slot * a.slot_stride + idx));
         }
       }
-      unsigned int m = 0u;
-      if (active) {
 #pragma unroll
-        for (int j = 1; j < DRC_MAX_R; ++j) {
+      for (int g = 0; g < 4; ++g) {
+        if (g < a.G && active) {
+          int r = 0;
 #pragma unroll
-          for (int i = 0; i < j; ++i) {
-            if (j < r) {
-              bool ne = (v[i].x != v[j].x) | (v[i].y != v[j].y) | (v[i].z != v[j].z) | (v[i].w != v[j].w);
-              m |= ne ? (1u << pair_bit(i, j)) : 0u;
-            }
+          for (int k = 0; k < 4; ++k) if (k < a.max_r && s_slot[g * a.max_r + k] >= 0) r = k + 1;
+          acc[g] |= pair_mask(v[g], r);
+        }
+      }
+    } else {
+      for (int g = 0; g < a.G; ++g) {
+        float4 v[DRC_MAX_R];
+        int r = 0;
+#pragma unroll
+        for (int k = 0; k < DRC_MAX_R; ++k) {
+          int slot = k < a.max_r ? s_slot[g * a.max_r + k] : -1;
+          if (slot >= 0) {
+            r = k + 1;
+            if (active) v[k] = ld_f4(reinterpret_cast<const float4*>(a.grad_in + slot * a.slot_stride + idx));
           }
         }
+        unsigned int m = active ? pair_mask(v, r) : 0u;
+        m = __reduce_or_sync(0xffffffffu, m);              // warp OR, then one global atomic per warp (mismatches are rare)
+        if ((threadIdx.x & 31) == 0 && m) atomicOr(&a.neq_mask[g * a.tv.ntensors + tensor], m);
       }
-      // warp OR, then one shared atomic per warp (mismatches are rare)
-      m = __reduce_or_sync(0xffffffffu, m);
-      if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_mask[g], m);
     }
-    __syncthreads();
-    if (threadIdx.x < a.G && s_mask[threadIdx.x])
-      atomicOr(&a.neq_mask[threadIdx.x * a.tv.ntensors + tensor], s_mask[threadIdx.x]);
-    __syncthreads();
   }
+  flush(cur_tensor);
 }
 
 struct ResolveArgs {
@@ -106,7 +152,8 @@ __global__ void vote_resolve_kernel(const __grid_constant__ ResolveArgs a) {
 
 extern "C" int drc_vote_compare(const VoteArgs* args, int grid, cudaStream_t stream) {
   if (args->max_r > DRC_MAX_R || args->G > DRC_MAX_WORKERS) return (int)cudaErrorInvalidValue;
-  vote_compare_kernel<<<grid, DRC_THREADS, 0, stream>>>(*args);
+  if (args->G <= 4 && args->max_r <= 4) vote_compare_kernel<true><<<grid, DRC_THREADS, 0, stream>>>(*args);
+  else vote_compare_kernel<false><<<grid, DRC_THREADS, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }
 
