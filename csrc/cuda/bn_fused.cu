@@ -437,3 +437,18 @@ extern "C" int drc_bn_bwd(const void* dy, const void* y, const void* x, const fl
   else bn_bwd_apply_kernel<2><<<grid, BN_THREADS, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }
+
+// Backward when the reduction already happened in the dgrad epilogue of the convolution that consumed this layer's output
+// (conv_epilogue.cuh, BatchNorm-backward mode): dz arrives masked, sums = [mean(dz), mean(dz * xhat)] -> only the apply kernel.
+extern "C" int drc_bn_bwd_apply(const void* dz, const void* x, const float* gamma, const float* mean, const float* invstd,
+                                const float* sums, void* dx, long long M, int C, int num_sms, cudaStream_t stream) {
+  if (!supported(C)) return -1;
+  BnBwdArgs a;
+  a.dy = (const __nv_bfloat16*)dz; a.y = nullptr; a.x = (const __nv_bfloat16*)x; a.gamma = gamma; a.beta = nullptr;
+  a.mean = mean; a.invstd = invstd; a.dx = (__nv_bfloat16*)dx; a.dres = nullptr; a.dgamma = nullptr; a.dbeta = nullptr;
+  a.partial = nullptr; a.sums = const_cast<float*>(sums); a.counter = nullptr; a.M = M; a.C = C; a.relu = 0;
+  int grid;
+  a.rows_per_cta = plan_rows(M, C, num_sms, false, &grid);
+  bn_bwd_apply_kernel<0><<<grid, BN_THREADS, 0, stream>>>(a);
+  return (int)cudaGetLastError();
+}

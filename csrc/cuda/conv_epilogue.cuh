@@ -11,6 +11,11 @@
 //      (atomic ticket) folds the slots in a fixed order with 16-byte loads and finalises mean / invstd / running statistics:
 //      the statistics pass of the BatchNorm (one full read of the activation + one launch per layer) disappears.
 //
+//   4. (dgrad, optional) BatchNorm BACKWARD reduction of the layer that produced this convolution's input: the dgrad output is the
+//      gradient of a BatchNorm(+ReLU) output y, so the epilogue masks it with y > 0 (dz), stores dz, and accumulates sum(dz) and
+//      sum(dz * xhat) per channel with the same register / partial / ticket machinery -- the reduce kernel of that BatchNorm's
+//      backward (one full read of dy, x and y + one launch) disappears and its apply kernel no longer needs the mask.
+//
 // Determinism: tile -> CTA assignment, in-CTA accumulation order and the slot fold order depend only on the problem shape and
 // the grid size, never on timing; replicas of a batch on different GPUs stay bit-identical (the exact-equality vote needs it).
 //
@@ -33,6 +38,14 @@ struct BnStatArgs {
   float* running_var;
   long long count;                // elements per channel (N * OH * OW)
   float eps, momentum;
+  // BatchNorm-backward mode (dgrad epilogue): non-null bwd_x switches the reduction to sum(dz), sum(dz * xhat)
+  const __nv_bfloat16* bwd_x;     // input x of the BatchNorm whose output fed this convolution (shape of the dgrad output)
+  const __nv_bfloat16* bwd_mask;  // that BatchNorm's output y (this convolution's forward input): dz = d * (y > 0); null = no ReLU
+  const float* bwd_mean;          // [C] batch statistics of that BatchNorm
+  const float* bwd_invstd;
+  float* bwd_sums;                // [2][C] out: mean(dz), mean(dz * xhat)   (what bn_bwd_apply_kernel consumes)
+  float* bwd_dgamma;              // [C] out: sum(dz * xhat)
+  float* bwd_dbeta;               // [C] out: sum(dz)
 };
 
 // shared-memory bytes the epilogue needs: staging tile + statistics accumulators
@@ -46,7 +59,10 @@ __host__ __device__ constexpr int stat_bytes() { return 4 * 2 * STAT_MAX_C * 4; 
 template <int BLOCK_N>
 __device__ __forceinline__ void drain_tile(uint32_t tmem_acc, uint8_t* sbuf, float* s_stat, int et, int valid_rows, int col0, int Cn,
                                            const float* bias_f32, const __nv_bfloat16* bias_bf16, uint64_t* tmem_empty_bar,
-                                           uint32_t remote_empty_bar = 0, const __nv_bfloat16* resid_row = nullptr) {
+                                           uint32_t remote_empty_bar = 0, const __nv_bfloat16* resid_row = nullptr,
+                                           const __nv_bfloat16* mask_row = nullptr) {
+  // mask_row: channel 0 of this thread's pixel in a tensor of the output's shape; the output is zeroed where it is <= 0 (ReLU
+  // backward of the BatchNorm output that fed this convolution), after the residual add
   // resid_row: channel 0 of THIS thread's output pixel in a tensor of the output's shape that is added to the tile before rounding
   // (dgrad: the gradient arriving over the other branch of a fork, e.g. the residual shortcut); null = nothing to add / row invalid
   const int q = et >> 5, lane = et & 31;
@@ -76,6 +92,22 @@ __device__ __forceinline__ void drain_tile(uint32_t tmem_acc, uint8_t* sbuf, flo
           const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) { const float2 g = __bfloat1622float2(rp[e]); f[jj * 8 + 2 * e] += g.x; f[jj * 8 + 2 * e + 1] += g.y; }
+        }
+      }
+    }
+    if (mask_row) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int cc = col0 + c + jj * 8;
+        if (cc < Cn) {
+          const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mask_row + cc));
+          const __nv_bfloat162* mp = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 g = __bfloat1622float2(mp[e]);
+            f[jj * 8 + 2 * e] = g.x > 0.f ? f[jj * 8 + 2 * e] : 0.f;
+            f[jj * 8 + 2 * e + 1] = g.y > 0.f ? f[jj * 8 + 2 * e + 1] : 0.f;
+          }
         }
       }
     }
@@ -125,6 +157,46 @@ struct StatAcc {
             const float2 f = __bfloat1622float2(p[e]);
             s[box * 8 + 2 * e] += f.x;          q[box * 8 + 2 * e] = fmaf(f.x, f.x, q[box * 8 + 2 * e]);
             s[box * 8 + 2 * e + 1] += f.y;      q[box * 8 + 2 * e + 1] = fmaf(f.y, f.y, q[box * 8 + 2 * e + 1]);
+          }
+        }
+      }
+    }
+  }
+  // BatchNorm-backward flavour: s += dz, q += dz * xhat with xhat = (x - mean) * invstd; dz is the staged (rounded, masked) tile,
+  // x is read from global memory -- row r of the tile lives at x + row_off(r) (channel 0 of that pixel), columns col0 + ...
+  template <typename RowOff>
+  __device__ __forceinline__ void add_tile_bwd(const uint8_t* sbuf, int et, int valid_rows, const __nv_bfloat16* x, RowOff row_off,
+                                               int col0, int Cn, const float* mean, const float* invstd) {
+    const int j = et & 7, rg = et >> 3;
+#pragma unroll
+    for (int box = 0; box < BLOCK_N / 64; ++box) {
+      const int cbase = col0 + box * 64 + j * 8;
+      if (cbase >= Cn) continue;
+      float mu[8], is[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { mu[e] = __ldg(mean + cbase + e); is[e] = __ldg(invstd + cbase + e); }
+      const uint8_t* base = sbuf + box * (128 * 128);
+      uint4 xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rg + 16 * i;
+        if (r < valid_rows) xv[i] = __ldg(reinterpret_cast<const uint4*>(x + row_off(r) + cbase));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rg + 16 * i;
+        if (r < valid_rows) {
+          const uint4 v = *reinterpret_cast<const uint4*>(base + r * 128 + ((j ^ (r & 7)) << 4));
+          const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+          const __nv_bfloat162* px = reinterpret_cast<const __nv_bfloat162*>(&xv[i]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 d = __bfloat1622float2(p[e]);
+            const float2 xx = __bfloat1622float2(px[e]);
+            s[box * 8 + 2 * e] += d.x;
+            q[box * 8 + 2 * e] = fmaf(d.x, (xx.x - mu[2 * e]) * is[2 * e], q[box * 8 + 2 * e]);
+            s[box * 8 + 2 * e + 1] += d.y;
+            q[box * 8 + 2 * e + 1] = fmaf(d.y, (xx.y - mu[2 * e + 1]) * is[2 * e + 1], q[box * 8 + 2 * e + 1]);
           }
         }
       }
@@ -220,6 +292,17 @@ __device__ __forceinline__ void finalize_stats(const BnStatArgs& st, float* s_st
   }
   __syncthreads();
   const float inv_m = 1.0f / (float)st.count;
+  if (st.bwd_x) {                                  // BatchNorm-backward mode: totals are sum(dz), sum(dz * xhat)
+    for (int i = threadIdx.x; i < width; i += NUM_THREADS) {
+      const int c = c_lo + i;
+      const float sd = s_stat[i], sq = s_stat[width + i];
+      st.bwd_dbeta[c] = sd;
+      st.bwd_dgamma[c] = sq;
+      st.bwd_sums[c] = sd * inv_m;
+      st.bwd_sums[Cn + c] = sq * inv_m;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < width; i += NUM_THREADS) {
     const int c = c_lo + i;
     const float m = s_stat[i] * inv_m;

@@ -148,17 +148,26 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     sacc.clear();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int w0 = (tile % wt) * TW, h0 = ((tile / wt) % ht) * TH, n0 = tile / (wt * ht);
+      if (want_stats && a.stat.bwd_x) {            // BatchNorm-backward mode: this tile's rows of x / y into L2 under the MMAs
+        const long long off = (((long long)n0 * a.H + (h0 + et / TW)) * a.W + (w0 + et % TW)) * BLOCK_N;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.stat.bwd_x + off));
+        if (a.stat.bwd_mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.stat.bwd_mask + off));
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const __nv_bfloat16* rrow = a.resid
-          ? a.resid + (((long long)n0 * a.H + (h0 + et / TW)) * a.W + (w0 + et % TW)) * BLOCK_N : nullptr;
+      auto row_off = [&](int r) -> long long { return (((long long)n0 * a.H + (h0 + r / TW)) * a.W + (w0 + r % TW)) * BLOCK_N; };
+      const __nv_bfloat16* rrow = a.resid ? a.resid + row_off(et) : nullptr;
+      const __nv_bfloat16* mrow = (want_stats && a.stat.bwd_mask) ? a.stat.bwd_mask + row_off(et) : nullptr;
       convepi::drain_tile<BLOCK_N>(tmem_base + (uint32_t)(acc * BLOCK_N), sbuf, s_stat, et, BLOCK_M, 0, BLOCK_N, a.bias_f32, a.bias_bf16,
-                                   &tmem_empty[acc], 0u, rrow);
+                                   &tmem_empty[acc], 0u, rrow, mrow);
       if (et == 0) {
         tma_store_4d(&tmap_out, sbuf, 0, w0, h0, n0);
         tma_store_commit();
       }
-      if (want_stats) sacc.add_tile(sbuf, et, BLOCK_M);
+      if (want_stats) {
+        if (a.stat.bwd_x) sacc.add_tile_bwd(sbuf, et, BLOCK_M, a.stat.bwd_x, row_off, 0, BLOCK_N, a.stat.bwd_mean, a.stat.bwd_invstd);
+        else sacc.add_tile(sbuf, et, BLOCK_M);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (want_stats) sacc.flush(s_stat, et, 0, BLOCK_N);
@@ -346,10 +355,12 @@ extern "C" int drc_conv_halo_stat_slots(int N, int H, int W, int num_sms) {
 // stat_*: optional fused BatchNorm statistics of the output (fprop only), see drc_convg.
 extern "C" int drc_conv_halo(const void* act, const void* wgt, void* out, int N, int H, int W, int dgrad, const float* bias_f32,
                              const void* bias_bf16, const void* resid, float* stat_partial, unsigned int* stat_counter, float* stat_mean,
-                             float* stat_invstd, float* running_mean, float* running_var, float eps, float momentum, int num_sms,
-                             int device, cudaStream_t stream) {
+                             float* stat_invstd, float* running_mean, float* running_var, float eps, float momentum,
+                             const void* bwd_x, const void* bwd_mask, const float* bwd_mean, const float* bwd_invstd, float* bwd_sums,
+                             float* bwd_dgamma, float* bwd_dbeta, int num_sms, int device, cudaStream_t stream) {
   if (!drc_conv_halo_supported(H, W, 64, 64)) return -1;
-  if (stat_partial && dgrad) return -4;
+  if (stat_partial && ((dgrad != 0) != (bwd_x != nullptr))) return -4;
+  if (bwd_x && !(stat_partial && bwd_mean && bwd_invstd && bwd_sums && bwd_dgamma && bwd_dbeta)) return -7;
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) return -2;
@@ -359,6 +370,8 @@ extern "C" int drc_conv_halo(const void* act, const void* wgt, void* out, int N,
   a.stat.partial = stat_partial; a.stat.counter = stat_counter; a.stat.mean = stat_mean; a.stat.invstd = stat_invstd;
   a.stat.running_mean = running_mean; a.stat.running_var = running_var; a.stat.count = (long long)N * H * W;
   a.stat.eps = eps; a.stat.momentum = momentum;
+  a.stat.bwd_x = (const __nv_bfloat16*)bwd_x; a.stat.bwd_mask = (const __nv_bfloat16*)bwd_mask; a.stat.bwd_mean = bwd_mean;
+  a.stat.bwd_invstd = bwd_invstd; a.stat.bwd_sums = bwd_sums; a.stat.bwd_dgamma = bwd_dgamma; a.stat.bwd_dbeta = bwd_dbeta;
   CUtensorMap tx, tw, tout;
   {
     cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};

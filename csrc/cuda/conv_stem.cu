@@ -279,6 +279,7 @@ extern "C" int drc_conv_stem_fprop(const void* x, const void* w, void* y, const 
   a.stat.partial = stat_partial; a.stat.counter = stat_counter; a.stat.mean = stat_mean; a.stat.invstd = stat_invstd;
   a.stat.running_mean = running_mean; a.stat.running_var = running_var; a.stat.count = (long long)N * H * W;
   a.stat.eps = eps; a.stat.momentum = momentum;
+  a.stat.bwd_x = nullptr; a.stat.bwd_mask = nullptr;           // forward statistics only
   stem_fprop_kernel<<<stem_grid(a.tiles, num_sms), THREADS, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }

@@ -288,19 +288,38 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       int cls, mt, n0;
       decode(unit, cls, mt, n0);
       const int w0 = (mt % wt) * a.BW, h0 = ((mt / wt) % ht) * a.BH, nb0 = (mt / (wt * ht)) * a.BN;
+      if (TMA_EPI && a.stat.bwd_x) {
+        // BatchNorm-backward mode: pull this tile's rows of y (mask) and x into L2 while the MMAs of the tile are still running --
+        // they were written by the forward pass long ago and would otherwise cost a DRAM round trip per epilogue step
+        const int rw = w0 + et % a.BW, rh = h0 + (et / a.BW) % a.BH, rn_ = nb0 + et / (a.BW * a.BH);
+        if (rn_ < a.N) {
+          const long long off = (((long long)rn_ * a.out_H + rh) * a.out_W + rw) * a.Cn + n0;
+#pragma unroll
+          for (int cb = 0; cb < BLOCK_N; cb += 64) {
+            if (n0 + cb < a.Cn) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.stat.bwd_x + off + cb));
+              if (a.stat.bwd_mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.stat.bwd_mask + off + cb));
+            }
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       if (dbg && et == 0) dbg[5] = clock64();
       tcgen05_fence_after();
       if (TMA_EPI) {
         int valid_rows = (a.N - nb0) * a.BW * a.BH;
         if (valid_rows > BLOCK_M) valid_rows = BLOCK_M;
-        const __nv_bfloat16* rrow = nullptr;
-        if (a.resid && et < valid_rows) {
-          const int rw = w0 + et % a.BW, rh = h0 + (et / a.BW) % a.BH, rn_ = nb0 + et / (a.BW * a.BH);
-          rrow = a.resid + (((long long)rn_ * a.out_H + rh) * a.out_W + rw) * a.Cn;
-        }
+        // element offset of channel 0 of tile row r in a tensor of the output's shape
+        auto row_off = [&](int r) -> long long {
+          const int rw = w0 + r % a.BW, rh = h0 + (r / a.BW) % a.BH, rn_ = nb0 + r / (a.BW * a.BH);
+          return (((long long)rn_ * a.out_H + rh) * a.out_W + rw) * a.Cn;
+        };
+        const bool row_ok = et < valid_rows;
+        const __nv_bfloat16* rrow = (a.resid && row_ok) ? a.resid + row_off(et) : nullptr;
+        const __nv_bfloat16* mrow = (a.stat.bwd_mask && row_ok) ? a.stat.bwd_mask + row_off(et) : nullptr;
         convepi::drain_tile<BLOCK_N>(tmem_base + (uint32_t)(acc * BLOCK_N), sbuf, s_stat, et, valid_rows, n0, a.Cn, a.bias_f32,
-                                     a.bias_bf16, &tmem_empty[acc], PAIR && !leader ? map_to_cta(&tmem_empty[acc], 0) : 0u, rrow);
+                                     a.bias_bf16, &tmem_empty[acc], PAIR && !leader ? map_to_cta(&tmem_empty[acc], 0) : 0u, rrow,
+                                     mrow);
         if (et == 0) {
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
@@ -308,7 +327,8 @@ convg_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           tma_store_commit();
         }
         if (want_stats) {
-          sacc.add_tile(sbuf, et, valid_rows);
+          if (a.stat.bwd_x) sacc.add_tile_bwd(sbuf, et, valid_rows, a.stat.bwd_x, row_off, n0, a.Cn, a.stat.bwd_mean, a.stat.bwd_invstd);
+          else sacc.add_tile(sbuf, et, valid_rows);
           stat_col0 = n0;
           if (!stat_keep) sacc.flush(s_stat, et, n0, a.Cn);
         }
@@ -765,7 +785,9 @@ extern "C" void drc_convg_set_timeline(long long* buf) { g_convg_dbg = buf; }
 extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int H, int W, int Cin, int Cout, int ks, int stride,
                          int dgrad, const float* bias_f32, const void* bias_bf16, const void* resid, int tma_store, float* stat_partial,
                          unsigned int* stat_counter, float* stat_mean, float* stat_invstd, float* running_mean, float* running_var,
-                         float eps, float momentum, int num_sms, int device, cudaStream_t stream) {
+                         float eps, float momentum, const void* bwd_x, const void* bwd_mask, const float* bwd_mean,
+                         const float* bwd_invstd, float* bwd_sums, float* bwd_dgamma, float* bwd_dbeta, int num_sms, int device,
+                         cudaStream_t stream) {
   if (!drc_convg_supported(H, W, Cin, Cout, ks, stride)) return -1;
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return (int)e; }
   const int OH = H / stride, OW = W / stride;
@@ -779,11 +801,17 @@ extern "C" int drc_convg(const void* act, const void* wgt, void* out, int N, int
   a.stat.partial = nullptr; a.stat.counter = stat_counter; a.stat.mean = stat_mean; a.stat.invstd = stat_invstd;
   a.stat.running_mean = running_mean; a.stat.running_var = running_var; a.stat.count = (long long)N * OH * OW;
   a.stat.eps = eps; a.stat.momentum = momentum;
+  a.stat.bwd_x = (const __nv_bfloat16*)bwd_x; a.stat.bwd_mask = (const __nv_bfloat16*)bwd_mask; a.stat.bwd_mean = bwd_mean;
+  a.stat.bwd_invstd = bwd_invstd; a.stat.bwd_sums = bwd_sums; a.stat.bwd_dgamma = bwd_dgamma; a.stat.bwd_dbeta = bwd_dbeta;
   const bool dense_out = !(dgrad && stride > 1);
   const bool tma_epi = tma_store && dense_out;
+  if (bwd_x && !(stat_partial && dgrad && bwd_mean && bwd_invstd && bwd_sums && bwd_dgamma && bwd_dbeta)) return -7;
   if (stat_partial) {
-    if (dgrad || !tma_epi || Cout > convepi::STAT_MAX_C || (Cout & 3)) return -4;
+    // forward statistics of y (fprop) or BatchNorm-backward sums of the layer that fed this convolution (dgrad + bwd_x)
+    if ((dgrad != 0) != (bwd_x != nullptr) || !tma_epi || a.Cn > convepi::STAT_MAX_C || (a.Cn & 3)) return -4;
     a.stat.partial = stat_partial;
+  } else {
+    a.stat.bwd_mask = nullptr;
   }
   const int m_tiles = (OW / a.BW) * (OH / a.BH) * ((N + a.BN - 1) / a.BN);
 

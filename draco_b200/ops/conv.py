@@ -86,7 +86,7 @@ def _lib():
         lib.drc_convg_plan.argtypes = [C.c_int] * 9 + [C.POINTER(C.c_int)]
         lib.drc_convg_plan.restype = C.c_int
         lib.drc_convg.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 8 + [N.ptr, N.ptr, N.ptr, C.c_int] + [N.ptr] * 6
-                                  + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
+                                  + [C.c_float, C.c_float] + [N.ptr] * 7 + [C.c_int, C.c_int, N.ptr])
         lib.drc_convg.restype = C.c_int
         lib.drc_convg_wgrad_supported.argtypes = [C.c_int] * 6
         lib.drc_convg_wgrad_supported.restype = C.c_int
@@ -99,7 +99,7 @@ def _lib():
         lib.drc_conv_halo_stat_slots.argtypes = [C.c_int] * 4
         lib.drc_conv_halo_stat_slots.restype = C.c_int
         lib.drc_conv_halo.argtypes = ([N.ptr, N.ptr, N.ptr] + [C.c_int] * 4 + [N.ptr, N.ptr, N.ptr] + [N.ptr] * 6
-                                      + [C.c_float, C.c_float, C.c_int, C.c_int, N.ptr])
+                                      + [C.c_float, C.c_float] + [N.ptr] * 7 + [C.c_int, C.c_int, N.ptr])
         lib.drc_conv_halo.restype = C.c_int
         lib.drc_conv_halo_wgrad.argtypes = [N.ptr] * 4 + [C.c_int] * 5 + [N.ptr]
         lib.drc_conv_halo_wgrad.restype = C.c_int
@@ -140,14 +140,48 @@ def _stat_args(req, cout: int, slots: int, device):
              req.momentum), (partial,))
 
 
+class BnBwdLink:
+    """Connects a fused BatchNorm(+ReLU) layer with the convolution that consumes its output, for the backward pass: the
+    convolution's dgrad epilogue masks its output with ``y > 0`` and reduces ``sum(dz)`` / ``sum(dz * xhat)`` per channel
+    (csrc/cuda/conv_epilogue.cuh, BatchNorm-backward mode), so the BatchNorm's backward only runs its apply kernel.
+    Created by ``ops.norm._BnActFn.forward`` (x, mean, invstd, relu), attached to the output tensor, picked up by
+    ``Conv2d.forward``; the dgrad fills ``dz`` / ``sums`` / ``dgamma`` / ``dbeta``.  Valid when that convolution (and its
+    ``fork``) is the only consumer of the BatchNorm output -- otherwise autograd hands the BatchNorm a different tensor than
+    ``dz`` and it falls back to its own reduction."""
+    __slots__ = ("x", "mean", "invstd", "relu", "dz", "sums", "dgamma", "dbeta")
+
+    def __init__(self, x, mean, invstd, relu):
+        self.x, self.mean, self.invstd, self.relu = x, mean, invstd, bool(relu)
+        self.dz = self.sums = self.dgamma = self.dbeta = None
+
+
+def _bwd_args(link, mask: torch.Tensor, c: int, slots: int, device):
+    """C-ABI tail (bwd_x, bwd_mask, bwd_mean, bwd_invstd, bwd_sums, bwd_dgamma, bwd_dbeta) + statistics head for a dgrad that
+    also reduces the BatchNorm backward of ``link``; without a link: null pointers."""
+    if link is None:
+        return (None,) * 7, None, ()
+    from .norm import _counter
+    partial = torch.empty(slots * 2 * c, dtype=torch.float32, device=device)
+    link.sums = torch.empty(2 * c, dtype=torch.float32, device=device)
+    link.dgamma = torch.empty(c, dtype=torch.float32, device=device)
+    link.dbeta = torch.empty(c, dtype=torch.float32, device=device)
+    head = (partial.data_ptr(), _counter(device)[16:].data_ptr(), None, None, None, None, 0.0, 0.0)
+    tail = (link.x.data_ptr(), mask.data_ptr() if link.relu else None, link.mean.data_ptr(), link.invstd.data_ptr(),
+            link.sums.data_ptr(), link.dgamma.data_ptr(), link.dbeta.data_ptr())
+    return tail, head, (partial,)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # tap-table implicit-GEMM kernels (csrc/cuda/conv_tap_tcgen05.cu): stride 1 or 2, 1x1 or 3x3, fprop / dgrad / split-K wgrad
 # ---------------------------------------------------------------------------------------------------------------------
 def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, dgrad: bool = False,
-                  bias: torch.Tensor = None, bn_stats: "BnStatRequest" = None, residual: torch.Tensor = None) -> torch.Tensor:
+                  bias: torch.Tensor = None, bn_stats: "BnStatRequest" = None, residual: torch.Tensor = None,
+                  bn_bwd=None) -> torch.Tensor:
     """``dgrad=False``: ``act`` = x [N, Cin, H, W] -> y [N, Cout, H/stride, W/stride];  ``dgrad=True``: ``act`` = dy -> dx.
     ``in_hw`` is the spatial size of the forward input x; ``weight`` [Cout, Cin, ks, ks] in channels-last storage.
-    ``residual``: channels-last bf16 tensor of the output's shape added in the epilogue (not for the 1x1 / stride-2 dgrad)."""
+    ``residual``: channels-last bf16 tensor of the output's shape added in the epilogue (not for the 1x1 / stride-2 dgrad).
+    ``bn_bwd`` = (BnBwdLink, y): stride-1 dgrad only -- the output is additionally masked with ``y > 0`` (y = the forward input of
+    this convolution = the linked BatchNorm's output) and the BatchNorm-backward sums are left on the link."""
     from .. import _native as N
     from . import kernels as K
     lib = _lib()
@@ -165,12 +199,18 @@ def convg_tcgen05(act: torch.Tensor, weight: torch.Tensor, in_hw, stride: int, d
     assert bn_stats is None or (tma and not dgrad)
     assert residual is None or (residual.shape == out.shape and residual.dtype == torch.bfloat16
                                 and residual.is_contiguous(memory_format=torch.channels_last))
-    slots = lib.drc_convg_stat_slots(n, h, w, cout, stride, sms) if bn_stats is not None else 0
+    slots = lib.drc_convg_stat_slots(n, h, w, cout, stride, sms) if (bn_stats is not None or bn_bwd is not None) else 0
     st, keep = _stat_args(bn_stats, cout, slots, act.device)
+    tail, head, keep2 = _bwd_args(bn_bwd[0], bn_bwd[1], cin, slots, act.device) if bn_bwd is not None else ((None,) * 7, None, ())
+    if bn_bwd is not None:
+        assert dgrad and stride == 1 and tma and bn_stats is None and bn_bwd[0].x.shape == out.shape
+        st = head
     N.check(lib.drc_convg(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, cin, cout, ks, stride, int(dgrad), bf32, bb16,
-                          residual.data_ptr() if residual is not None else None, tma, *st, sms, act.device.index,
+                          residual.data_ptr() if residual is not None else None, tma, *st, *tail, sms, act.device.index,
                           torch.cuda.current_stream().cuda_stream), "convg")
-    del keep
+    del keep, keep2
+    if bn_bwd is not None:
+        bn_bwd[0].dz = out
     return out
 
 
@@ -209,7 +249,7 @@ def halo_supported(h: int, w: int, cin: int, cout: int) -> bool:
 
 
 def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, bias: torch.Tensor = None,
-                 bn_stats: "BnStatRequest" = None, residual: torch.Tensor = None) -> torch.Tensor:
+                 bn_stats: "BnStatRequest" = None, residual: torch.Tensor = None, bn_bwd=None) -> torch.Tensor:
     from .. import _native as N
     from . import kernels as K
     lib = _lib()
@@ -219,14 +259,20 @@ def conv3x3_halo(act: torch.Tensor, weight: torch.Tensor, dgrad: bool = False, b
     bf32 = bias.data_ptr() if bias is not None and bias.dtype == torch.float32 else None
     bb16 = bias.data_ptr() if bias is not None and bias.dtype == torch.bfloat16 else None
     sms = K.sm_count(act.device)
-    slots = lib.drc_conv_halo_stat_slots(n, h, w, sms) if bn_stats is not None else 0
+    slots = lib.drc_conv_halo_stat_slots(n, h, w, sms) if (bn_stats is not None or bn_bwd is not None) else 0
     st, keep = _stat_args(bn_stats, 64, slots, act.device)
+    tail, head, keep2 = _bwd_args(bn_bwd[0], bn_bwd[1], 64, slots, act.device) if bn_bwd is not None else ((None,) * 7, None, ())
+    if bn_bwd is not None:
+        assert dgrad and bn_stats is None and bn_bwd[0].x.shape == out.shape
+        st = head
     assert residual is None or (residual.shape == out.shape and residual.dtype == torch.bfloat16
                                 and residual.is_contiguous(memory_format=torch.channels_last))
     N.check(lib.drc_conv_halo(act.data_ptr(), weight.data_ptr(), out.data_ptr(), n, h, w, int(dgrad), bf32, bb16,
-                              residual.data_ptr() if residual is not None else None, *st, sms,
+                              residual.data_ptr() if residual is not None else None, *st, *tail, sms,
                               act.device.index, torch.cuda.current_stream().cuda_stream), "conv_halo")
-    del keep
+    del keep, keep2
+    if bn_bwd is not None:
+        bn_bwd[0].dz = out
     return out
 
 
@@ -313,8 +359,15 @@ class _ConvGFn(torch.autograd.Function):
     inside the dgrad kernel's epilogue instead of by a separate elementwise kernel of autograd."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, bn_req, fork=False):
+    def forward(ctx, x, weight, bias, stride, bn_req, fork=False, in_link=None):
         ctx.save_for_backward(x, weight)
+        # the BatchNorm(+ReLU) layer whose output x is: its backward reduction rides on this layer's dgrad epilogue (stride 1,
+        # TMA-store epilogue, <= 512 channels)
+        ctx.in_link = in_link if (in_link is not None and stride == 1 and weight.shape[1] <= 512
+                                  and os.environ.get("DRACO_CONV_EPI", "tma") != "direct"
+                                  and os.environ.get("DRACO_BN_BWD_FUSE", "0") == "1" and in_link.x.shape == x.shape) else None
+        # OPT-IN: measured on B200 (profiles/README.md, "what did not work") the fused epilogue costs 8-9 us per tile (row-offset
+        # integer divisions + exposed loads of y / x) against the 11 us reduce kernel it removes: the step gets 6 % slower
         ctx.stride, ctx.has_bias = stride, bias is not None
         ctx.set_materialize_grads(False)          # no zero-filled "gradients" for the statistics outputs
         h, w = x.shape[2], x.shape[3]
@@ -335,7 +388,7 @@ class _ConvGFn(torch.autograd.Function):
     def backward(ctx, dy, _dmean, _dinvstd, dfork):
         x, weight = ctx.saved_tensors
         if dy is None:                                # only the fork branch carried a gradient
-            return dfork, None, None, None, None, None
+            return dfork, None, None, None, None, None, None
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         if dfork is not None and dfork.numel() == 0:
@@ -362,17 +415,19 @@ class _ConvGFn(torch.autograd.Function):
                 x.record_stream(side)
         if ctx.needs_input_grad[0]:
             res = dfork if fuse_fork else None
+            link = ctx.in_link if (dfork is None or fuse_fork) else None       # the mask has to see the complete gradient of x
+            bb = (link, x) if link is not None else None
             if ctx.halo:
-                dx = conv3x3_halo(dy, weight, True, None, None, res)
+                dx = conv3x3_halo(dy, weight, True, None, None, res, bb)
             else:
-                dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True, None, None, res)
+                dx = convg_tcgen05(dy, weight, x.shape[2:], ctx.stride, True, None, None, res, bb)
             if dfork is not None and not fuse_fork:
                 dx = dx + dfork
         if ctx.needs_input_grad[1] and dw is None:
             dw = wgrad()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum((0, 2, 3))
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class Conv2d(nn.Conv2d):
@@ -418,7 +473,8 @@ class Conv2d(nn.Conv2d):
             if self._tap_ok(x) and x.requires_grad and os.environ.get("DRACO_CONV_FORK", "1") != "0":
                 backend_counters["tcgen05"] += 1
                 req = bn.stat_request(x, self.out_channels) if (bn is not None and hasattr(bn, "stat_request")) else None
-                y, mean, invstd, xf = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req, True)
+                y, mean, invstd, xf = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req, True,
+                                                     getattr(x, "_draco_bn_link", None))
                 if req is not None:
                     bn.pending_stats = (y, mean, invstd)
                 return y, xf
@@ -433,7 +489,8 @@ class Conv2d(nn.Conv2d):
         if self._tap_ok(x):
             backend_counters["tcgen05"] += 1
             req = bn.stat_request(x, self.out_channels) if (bn is not None and hasattr(bn, "stat_request")) else None
-            y, mean, invstd, _ = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req)
+            y, mean, invstd, _ = _ConvGFn.apply(x, self.weight, self.bias, self.stride[0], req, False,
+                                                getattr(x, "_draco_bn_link", None) if x.requires_grad else None)
             if req is not None:
                 bn.pending_stats = (y, mean, invstd)
             return y

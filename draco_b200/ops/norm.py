@@ -35,6 +35,8 @@ def _lib():
         lib.drc_bn_fwd.restype = C.c_int
         lib.drc_bn_bwd.argtypes = [N.ptr] * 14 + [N.i64, C.c_int, C.c_int, C.c_int, st]
         lib.drc_bn_bwd.restype = C.c_int
+        lib.drc_bn_bwd_apply.argtypes = [N.ptr] * 7 + [N.i64, C.c_int, C.c_int, st]
+        lib.drc_bn_bwd_apply.restype = C.c_int
         lib._bn_ready = True
     return lib
 
@@ -92,7 +94,7 @@ def fused_supported(x: torch.Tensor, training: bool) -> bool:
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu, mean, invstd):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu, mean, invstd, link_box=None):
         """``mean`` / ``invstd`` given: statistics came out of the producing convolution's epilogue, only the apply kernel runs."""
         lib = _lib()
         n, c, h, w = x.shape
@@ -119,6 +121,10 @@ class _BnActFn(torch.autograd.Function):
         mask_from_x = residual is None and os.environ.get("DRACO_BN_MASK", "y") == "x"
         ctx.save_for_backward(x, y if (relu and not mask_from_x) else None, gamma, beta, mean, invstd)
         ctx.relu, ctx.has_res = bool(relu), residual is not None
+        ctx.link = None
+        if link_box is not None:                       # see ops.conv.BnBwdLink: the consumer convolution may reduce for us
+            from .conv import BnBwdLink
+            ctx.link = link_box[0] = BnBwdLink(x, mean, invstd, relu)
         return y
 
     @staticmethod
@@ -131,6 +137,17 @@ class _BnActFn(torch.autograd.Function):
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
+        link, ctx.link = ctx.link, None
+        if link is not None and link.sums is not None and link.dz is not None and link.dz.data_ptr() == dy.data_ptr():
+            # the consuming convolution's dgrad epilogue already masked dy (dz) and reduced sum(dz), sum(dz * xhat): apply only
+            backend_counters["bwd_in_conv"] = backend_counters.get("bwd_in_conv", 0) + 1
+            torch.cuda.set_device(dev)
+            N.check(lib.drc_bn_bwd_apply(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                         link.sums.data_ptr(), dx.data_ptr(), M, c, _sms(dev),
+                                         torch.cuda.current_stream().cuda_stream), "bn_bwd_apply")
+            dgamma, dbeta = link.dgamma, link.dbeta
+            link.dz = link.sums = None
+            return dx, (dy if ctx.has_res else None), dgamma, dbeta, None, None, None, None, None, None, None, None
         dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
@@ -141,7 +158,7 @@ class _BnActFn(torch.autograd.Function):
                                dx.data_ptr(), _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), sums.data_ptr(),
                                _counter(dev)[8:].data_ptr(), M, c, int(ctx.relu), _sms(dev),
                                torch.cuda.current_stream().cuda_stream), "bn_bwd")
-        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 class FusedBatchNorm2d(nn.BatchNorm2d):
@@ -182,9 +199,13 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
             if pend is not None and pend[0] is x:
                 mean, invstd = pend[1], pend[2]                   # running statistics were updated by the convolution
                 backend_counters["conv_stats"] = backend_counters.get("conv_stats", 0) + 1
-            return _BnActFn.apply(x, residual, self.weight, self.bias, self.running_mean if upd else None,
-                                  self.running_var if upd else None, self.eps,
-                                  self.momentum if self.momentum is not None else 0.1, relu, mean, invstd)
+            box = [None] if x.requires_grad else None
+            y = _BnActFn.apply(x, residual, self.weight, self.bias, self.running_mean if upd else None,
+                               self.running_var if upd else None, self.eps,
+                               self.momentum if self.momentum is not None else 0.1, relu, mean, invstd, box)
+            if box is not None and box[0] is not None:
+                y._draco_bn_link = box[0]              # picked up by the ops.conv.Conv2d that consumes y (BatchNorm backward in its dgrad)
+            return y
         assert pend is None, "a convolution produced fused statistics for a BatchNorm call that cannot use them"
         backend_counters["aten"] += 1
         if self.training and not UPDATE_RUNNING_STATS:

@@ -410,3 +410,44 @@ def test_resnet_block_conv_bn_fusion_matches_unfused(monkeypatch):
         outs.append((y.detach().float(), xi.grad.float(), blk.conv1.weight.grad.float(), blk.bn2.running_var.clone()))
     for a, b in zip(*outs):
         assert _rel_err(a, b) < 2e-2, _rel_err(a, b)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("planes,hw,n", [(64, 32, 32), (128, 16, 16), (256, 8, 128), (512, 4, 24)])
+def test_batchnorm_backward_reduction_inside_the_dgrad_epilogue(planes, hw, n, monkeypatch):
+    """Two stacked BasicBlocks: the BatchNorm backward reductions (sum dz, sum dz * xhat) of the layers whose output feeds a
+    stride-1 convolution can ride on that convolution's dgrad epilogue (DRACO_BN_BWD_FUSE=1; halo and tap kernels, with the
+    residual-fork gradient added first), so those BatchNorms only run their apply kernel.  Same result as the standalone reduce
+    kernels up to summation order; deterministic; the counter proves the fused path ran.  (Opt-in: measured slower.)"""
+    from draco_b200.models.resnet import BasicBlock
+    from draco_b200.ops import norm
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(planes + hw)
+    net = torch.nn.Sequential(BasicBlock(planes, planes, 1), BasicBlock(planes, planes, 1)).to(dev)
+    for m in net.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.to(torch.bfloat16)
+    net = net.to(memory_format=torch.channels_last)
+    bn0 = norm.FusedBatchNorm2d(planes).to(dev)
+    x = _cl(torch.randn(n, planes, hw, hw, device=dev))
+    gy = _cl(torch.randn(n, planes, hw, hw, device=dev))
+    runs = {}
+    for mode in ("1", "0", "1"):
+        monkeypatch.setenv("DRACO_BN_BWD_FUSE", mode)
+        net.zero_grad()
+        bn0.zero_grad()
+        before = norm.backend_counters.get("bwd_in_conv", 0)
+        xi = x.clone().requires_grad_(True)
+        y = net(bn0(xi, relu=True))            # bn0 -> block1.conv1 (fork) ; block1.bn1 -> conv2 ; block1 out -> block2.conv1 (fork) ; ...
+        y.backward(gy)
+        used = norm.backend_counters.get("bwd_in_conv", 0) - before
+        assert used == (4 if mode == "1" else 0), used          # bn0, block1.bn1, block1.bn2 (block output), block2.bn1
+        got = [xi.grad.float(), bn0.weight.grad.clone(), bn0.bias.grad.clone(), net[0].bn1.weight.grad.clone(),
+               net[0].bn2.weight.grad.clone(), net[0].bn2.bias.grad.clone(), net[0].conv1.weight.grad.float(),
+               net[1].bn1.bias.grad.clone()]
+        if mode in runs:
+            for a, b in zip(runs[mode], got):
+                assert torch.equal(a, b)                          # deterministic
+        runs[mode] = got
+    for a, b in zip(runs["1"], runs["0"]):
+        assert _rel_err(a, b) < 2e-2, _rel_err(a, b)

@@ -124,6 +124,7 @@ for (c, hw) in [(64, 32), (128, 16), (256, 8), (512, 4)]:
     class _Ctx:
         saved_tensors = (x, None, bn.weight, bn.bias, mean, invstd)
         relu, has_res = True, False
+        link = None
     ctx_stub = _Ctx()
 
     row = {"layer": f"bn+relu C={c} {hw}x{hw}", "MB": round(x.numel() * 2 / 1e6, 1), "fwd_apply_only_us": timeit(fwd_given),

@@ -19,10 +19,11 @@ os.makedirs(out_dir, exist_ok=True)
 from draco_b200.ops import conv as _C  # noqa: E402
 MODES = os.environ.get("WORKER_MODES", "fused,fused_wgrad_stream,aten").split(",")
 for mode in MODES:
-    # fused[_wgrad_stream][_nofork][_maskx]: A/B switches of single optimisations, same process, same box
+    # fused[_wgrad_stream][_nofork][_maskx][_bnfuse]: A/B switches of single optimisations, same process, same box
     os.environ["DRACO_BN"] = "aten" if mode == "aten" else "fused"
     os.environ["DRACO_CONV_FORK"] = "0" if "nofork" in mode else "1"
     os.environ["DRACO_BN_MASK"] = "x" if "maskx" in mode else "y"
+    os.environ["DRACO_BN_BWD_FUSE"] = "1" if "bnfuse" in mode else "0"
     _C.WGRAD_SIDE_STREAM = "wgrad_stream" in mode
     cfg = JobConfig(network=net, dataset="Cifar10", approach="baseline", mode="normal", batch_size=128, num_workers=1,
                     dtype="bf16", synthetic_size=1024, transport="nvl").resolve(1)

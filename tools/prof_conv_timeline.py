@@ -33,9 +33,15 @@ for (c, k, hw, ks, st) in [(128, 128, 16, 3, 1), (256, 256, 8, 3, 1), (512, 512,
     x = cl(torch.randn(N, c, hw, hw, device=dev))
     w = wt(k, c, ks)
     dy = cl(torch.randn(N, k, hw // st, hw // st, device=dev))
+    xbn = cl(torch.randn(N, c, hw, hw, device=dev))
+    mean, invstd = torch.zeros(c, device=dev), torch.ones(c, device=dev)
     for name, fn in (("fprop", lambda: CV.convg_tcgen05(x, w, (hw, hw), st)),
                      ("fprop+stats", lambda: CV.convg_tcgen05(x, w, (hw, hw), st, False, None, CV.BnStatRequest(1e-5, 0.1))),
-                     ("dgrad", lambda: CV.convg_tcgen05(dy, w, (hw, hw), st, True))):
+                     ("dgrad", lambda: CV.convg_tcgen05(dy, w, (hw, hw), st, True)),
+                     ("dgrad+bnbwd", (lambda: CV.convg_tcgen05(dy, w, (hw, hw), st, True, None, None, None,
+                                                                (CV.BnBwdLink(xbn, mean, invstd, True), x))) if st == 1 else None)):
+        if fn is None:
+            continue
         for _ in range(3):
             fn()
         buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
