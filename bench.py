@@ -66,19 +66,26 @@ def parse():
     ap.add_argument("--timeline", type=str, default=None,
                     help="after the timed runs, record 3 steps under torch.profiler and write <FILE>.rank<R>.txt: every kernel of "
                          "this rank's GPU in start order (start us, duration us, stream, name) -- NOT a timed number")
+    ap.add_argument("--timeline-e2e", type=str, default=None,
+                    help="like --timeline but for 3 steps of the end-to-end loop (Trainer.train_step_pipelined, pinned H2D + D2H)")
     ap.add_argument("--worker-streams", type=int, default=None,
                     help="concurrent CUDA streams for logical workers sharing a GPU (default: the JobConfig default)")
     return ap.parse_args()
 
 
-def _write_timeline(path, trainer, rank, barrier):
+def _write_timeline(path, trainer, rank, barrier, pipelined=False):
     """Kernel timeline of 3 consecutive steps on this rank's GPU (CUPTI through torch.profiler; graph replays included)."""
     import torch
     from torch.profiler import ProfilerActivity, profile
     barrier()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(3):
-            trainer.train_step_async()
+            if pipelined:
+                trainer.train_step_pipelined()
+            else:
+                trainer.train_step_async()
+        if pipelined:
+            trainer.drain()
         torch.cuda.synchronize()
     barrier()
     raw = f"{path}.rank{rank}.trace.json"
@@ -195,6 +202,8 @@ def main() -> int:
         h2d = reduce_sum(float(eng.worker.h2d_bytes if eng.local_workers else 0))
         # loss/prec1/prec5 + watchdog word + the step's device-side phase stamps (12 x int64)
         d2h = reduce_sum((12.0 if eng.local_workers else 0.0) + (4.0 + 96.0 if a.impl == "ours" else 0.0))
+        if a.timeline_e2e:
+            _write_timeline(a.timeline_e2e, trainer, rank, barrier, pipelined=True)
         e2e = {"value": a.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "final_loss": mean_loss(last),
                "api": "Trainer.train_step_pipelined() + drain()",

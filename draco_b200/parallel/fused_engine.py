@@ -482,7 +482,7 @@ class FusedEngine:
             return self.worker.stage_batches(step)
         return 0
 
-    def train_step(self, stage: bool = True) -> None:
+    def train_step(self, stage: bool = True, prefetch: bool = True) -> None:
         """Enqueue exactly one full step for this process (asynchronous; ``read_metrics``/``synchronize`` wait).
         With CUDA graphs the first two steps run eagerly, the third call captures, and from then on a step is one
         graph replay (plus the input staging copies)."""
@@ -503,9 +503,15 @@ class FusedEngine:
             if self.debug_checksum:
                 self._verify_checksums(self.step)
         self.step += 1
-        if stage:
-            # prefetch: gather the next step's batches on the CPU while the GPU runs this step; the H2D copies are
-            # stream-ordered after the step that was just enqueued, so they cannot overwrite inputs still in use
+        if stage and prefetch:
+            self.prefetch_inputs()
+
+    def prefetch_inputs(self) -> None:
+        """Gather the next step's batches on the CPU and start their H2D copy (copy stream) while the GPU runs the step that was
+        just enqueued; the device-to-device hand-over into the step's input buffers is stream-ordered after that step, so it cannot
+        overwrite inputs still in use.  ``train_step(prefetch=False)`` + this call lets a caller enqueue other work (the
+        metrics D2H of the step) between the two."""
+        if self.active and self._staged_step != self.step:
             self._stage(self.step)
             self._staged_step = self.step
 

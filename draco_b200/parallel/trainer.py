@@ -98,8 +98,14 @@ class Trainer:
         the step is enqueued, the D2H copy of its loss / Prec@k is enqueued behind it, and the metrics of the PREVIOUS
         step are returned (``None`` on the first call).  Every step's result is still read by the host -- one step late --
         but the GPU never idles waiting for the host to look at a loss.  ``drain()`` returns the last one."""
-        self.engine.train_step(stage=True)
-        handle = self.engine.enqueue_metrics_read()
+        eng = self.engine
+        if hasattr(eng, "prefetch_inputs"):
+            eng.train_step(stage=True, prefetch=False)
+            handle = eng.enqueue_metrics_read()            # the small D2H copies go first: they would queue behind the input H2D
+            eng.prefetch_inputs()
+        else:
+            eng.train_step(stage=True)
+            handle = eng.enqueue_metrics_read()
         prev, self._pending = getattr(self, "_pending", None), (self.engine.step - 1, handle)
         return self.engine.resolve_metrics(prev[1]) if prev is not None else None
 

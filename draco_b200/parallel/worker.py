@@ -193,13 +193,34 @@ class WorkerCompute:
                 i += 1
         if loader is not None:
             loader.wait()
-        self._x_all.copy_(px, non_blocking=True)
-        self._y_all.copy_(py, non_blocking=True)
         nbytes = px.numel() + py.numel() * 8
         if self.device.type == "cuda":
-            ev = self._pin_events[slot] or torch.cuda.Event(blocking=True)
-            ev.record()
-            self._pin_events[slot] = ev
+            # The PCIe transfer runs on a COPY STREAM into device staging buffers while the compute stream still executes the
+            # step that was enqueued before this call; the compute stream then only does a device-to-device copy (a few us)
+            # into the buffers the captured step reads.  In-stream H2D copies cost ~40 us of idle GPU per step.
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._x_stage, self._y_stage = torch.empty_like(self._x_all), torch.empty_like(self._y_all)
+                self._stage_free = torch.cuda.Event()        # staging buffers consumed by the last D2D
+                self._stage_full = torch.cuda.Event()
+                self._stage_free.record(main)
+            cs = self._copy_stream
+            cs.wait_event(self._stage_free)
+            with torch.cuda.stream(cs):
+                self._x_stage.copy_(px, non_blocking=True)
+                self._y_stage.copy_(py, non_blocking=True)
+                ev = self._pin_events[slot] or torch.cuda.Event(blocking=True)
+                ev.record(cs)                                # pinned slot reusable (host waits on it two stagings later)
+                self._pin_events[slot] = ev
+                self._stage_full.record(cs)
+            main.wait_event(self._stage_full)
+            self._x_all.copy_(self._x_stage, non_blocking=True)
+            self._y_all.copy_(self._y_stage, non_blocking=True)
+            self._stage_free.record(main)
+        else:
+            self._x_all.copy_(px)
+            self._y_all.copy_(py)
         self.h2d_bytes = nbytes
         return nbytes
 

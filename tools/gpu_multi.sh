@@ -12,6 +12,7 @@ for s in "$@"; do
   case $s in
     bench)      timeout -k 10 900 $TR --master-port 29611 bench.py --gpus $N --steps 30 --warmup 5 > $OUT/bench_ours.log 2> $OUT/bench_ours.err; echo "bench rc=$?" ;;
     timeline)   timeout -k 10 600 $TR --master-port 29615 bench.py --gpus $N --steps 10 --warmup 5 --skip-e2e --sanity-steps 0 --timeline $OUT/timeline $TIMELINE_ARGS > $OUT/timeline.log 2>&1; echo "timeline rc=$?" ;;
+    timeline_e2e) timeout -k 10 600 $TR --master-port 29621 bench.py --gpus $N --steps 10 --warmup 5 --sanity-steps 0 --timeline-e2e $OUT/timeline_e2e $TIMELINE_ARGS > $OUT/timeline_e2e.log 2>&1; echo "timeline_e2e rc=$?" ;;
     bench_flat) timeout -k 10 900 $TR --master-port 29612 bench.py --gpus $N --steps 30 --warmup 5 --impl nccl_flat > $OUT/bench_flat.log 2> $OUT/bench_flat.err; echo "bench_flat rc=$?" ;;
     bench_nccl) timeout -k 10 900 $TR --master-port 29613 bench.py --gpus $N --steps 10 --warmup 3 --impl nccl > $OUT/bench_nccl.log 2> $OUT/bench_nccl.err; echo "bench_nccl rc=$?" ;;
     bench_wf1)  timeout -k 10 900 $TR --master-port 29614 bench.py --gpus $N --steps 30 --warmup 5 --worker-fail 1 --sanity-steps 0 > $OUT/bench_ours_wf1.log 2> $OUT/bench_ours_wf1.err; echo "bench_wf1 rc=$?" ;;
