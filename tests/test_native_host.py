@@ -138,7 +138,7 @@ def test_native_loader_thread_pool_overlapping_jobs():
 # ------------------------------------------------------------------------------------------------ tap-table convolution algebra
 @pytest.mark.parametrize("ks,stride", [(3, 1), (3, 2), (1, 2), (1, 1)])
 def test_conv_tap_tables_reproduce_fprop_and_parity_class_dgrad(ks, stride):
-    """The host-side tables that drive the tap-table tcgen05 convolutions (csrc/cuda/conv_strided_tcgen05.cu), checked by
+    """The host-side tables that drive the tap-table tcgen05 convolutions (csrc/cuda/conv_tap_tcgen05.cu), checked by
     emulating the kernel's loads on the CPU: input pixel = patch origin * in_mul + tap offset (out-of-range reads as zero, as
     the TMA unit fills), one weight column block per tap; strided dgrad assembled from its parity classes."""
     import torch
@@ -197,3 +197,28 @@ def test_conv_tap_tables_reproduce_fprop_and_parity_class_dgrad(ks, stride):
     dref = torch.nn.grad.conv2d_input((n, cin, H, H), w.permute(0, 3, 1, 2), dy.permute(0, 3, 1, 2), stride=stride,
                                       padding=pad).permute(0, 2, 3, 1)
     assert torch.allclose(dx, dref, atol=1e-10)
+
+
+def test_tap_convolution_launch_plans(monkeypatch):
+    """Host-side planning of the tap convolution (drc_convg_plan): one CTA per tile by default (the multicast-cluster and CTA-pair
+    variants measured slower on B200), the forced shapes honour divisibility, grids are whole clusters within the SM count."""
+    if not N.cuda_available():
+        pytest.skip("libdraco_cuda.so not built")
+    from draco_b200.ops.conv import convg_plan
+    monkeypatch.delenv("DRACO_CONV_CLUSTER", raising=False)
+    layers = [(128, 16, 16, 128, 128, 3, 1), (128, 8, 8, 256, 256, 3, 1), (128, 4, 4, 512, 512, 3, 1), (128, 32, 32, 64, 128, 3, 2),
+              (32, 56, 56, 64, 64, 3, 1), (32, 14, 14, 256, 256, 3, 1)]
+    for (n, h, w, cin, cout, ks, st) in layers:
+        for dgrad in (0, 1):
+            bn, cm, cn, grid, mode = convg_plan(n, h, w, cin, cout, ks, st, dgrad)
+            assert (cm, cn, mode) == (1, 1, 0) and 0 < grid <= 148
+            assert bn == (128 if (cin if dgrad else cout) >= 128 else 64)
+    monkeypatch.setenv("DRACO_CONV_CLUSTER", "pair")
+    bn, cm, cn, grid, mode = convg_plan(128, 8, 8, 256, 256, 3, 1, 0)
+    assert (bn, cm, cn, mode) == (128, 2, 1, 2) and grid % 2 == 0 and grid <= 148
+    monkeypatch.setenv("DRACO_CONV_CLUSTER", "2,2,128")
+    bn, cm, cn, grid, mode = convg_plan(128, 8, 8, 256, 256, 3, 1, 1)
+    assert (bn, cm, cn, mode) == (128, 2, 2, 1) and grid % 4 == 0
+    monkeypatch.setenv("DRACO_CONV_CLUSTER", "1,4,128")          # 128 output channels = one N tile: cn = 4 is not realisable
+    assert convg_plan(128, 16, 16, 128, 128, 3, 1, 0)[1:3] != [1, 4]
+    assert convg_plan(128, 15, 16, 128, 128, 3, 3, 0) is None     # unsupported geometry
