@@ -14,8 +14,10 @@ def main(path, out, title):
             continue
         v = float(row["Metric Value"].replace(",", ""))
         v = v / 1e3 if row["Metric Unit"] == "ns" else v * 1e3 if row["Metric Unit"] == "ms" else v
-        name = re.sub(r"<.*", "", row["Kernel Name"])
-        name = re.sub(r"^void ", "", name)[:80]
+        name = re.sub(r"^void ", "", row["Kernel Name"]).replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+        name = re.sub(r"\(.*$", "", name)                       # drop the argument list, keep template arguments
+        name = re.sub(r"^at::native::(\(anonymous namespace\)::)?", "at::", name)
+        name = re.sub(r"<.*", "", name)[:90] if name.startswith("at::") else name[:90]
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1; a[1] += v; tot += v; n += 1
     with open(out, "w") as fh:
