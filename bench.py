@@ -61,7 +61,7 @@ def parse():
                     help="after the timed runs: train the same job for this many steps with ONE liar (which r=3 provably tolerates) "
                          "and with none, and report that the loss is finite and identical (0 = skip)")
     ap.add_argument("--wgrad-stream", type=str, default="auto", choices=("auto", "on", "off"),
-                    help="weight-gradient kernels on a side stream (auto: processes that host one worker)")
+                    help="weight-gradient kernels on a low-priority side stream (auto = on)")
     ap.add_argument("--ps-stream", action="store_true", help="co-located PS on its own stream inside the captured graph")
     ap.add_argument("--timeline", type=str, default=None,
                     help="after the timed runs, record 3 steps under torch.profiler and write <FILE>.rank<R>.txt: every kernel of "

@@ -63,7 +63,7 @@ class JobConfig:
     debug_checksum: bool = False    # verify every pushed gradient: loopback re-encode vs what landed in the PS slot (eager mode)
     profile_phases: bool = False    # CUDA-event timers per phase (fetch/comp/encode/comm/decode/update); disables CUDA graphs
     multicast: str = "auto"         # auto | on | off  (NVLS multimem.st broadcast)
-    wgrad_stream: str = "auto"      # weight-gradient kernels on a side stream: auto (processes hosting ONE worker) | on | off
+    wgrad_stream: str = "auto"      # weight-gradient kernels on a low-priority side stream: auto (= on with zero-copy gradients) | on | off
     spin_timeout_s: float = 60.0
     ps_stream: bool = False         # PS co-located with workers consumes gradient buckets on its own stream (captured graph only).
                                     # Off by default: its spin-wait kernels then depend on kernels of OTHER graph branches making

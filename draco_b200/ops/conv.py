@@ -29,6 +29,9 @@ backend_counters = {"tcgen05": 0, "cudnn": 0}
 WGRAD_SIDE_STREAM = False
 _side_streams = {}
 _side_pending = set()        # keys whose side stream holds work the backward stream has not joined yet
+_side_keep = {}              # key -> tensors the side stream still reads (dy, x): kept alive until the forking stream has joined, so
+                             # that the caching allocator cannot hand their memory to a later kernel of the forking stream while a
+                             # weight-gradient kernel is still reading it (inside a CUDA-graph capture record_stream() does not help)
 
 
 def _wgrad_stream(device) -> "torch.cuda.Stream":
@@ -50,6 +53,7 @@ def join_wgrad_stream(device, waiter: "torch.cuda.Stream" = None) -> None:
     (waiter or cur).wait_stream(_side_streams[key])
     if waiter is None or waiter.cuda_stream == cur.cuda_stream:
         _side_pending.discard(key)
+        _side_keep.pop(key, None)                  # the forking stream is ordered after every wgrad: their inputs may be reused
 
 
 class _Conv1x1Fn(torch.autograd.Function):
@@ -409,10 +413,9 @@ class _ConvGFn(torch.autograd.Function):
             cur = torch.cuda.current_stream(dy.device)
             with torch.cuda.stream(side):
                 dw = wgrad()
+            _side_keep.setdefault((dy.device, cur.cuda_stream), []).extend((dy, x))     # alive until join_wgrad_stream()
             if not torch.cuda.is_current_stream_capturing():
                 dw.record_stream(cur)              # allocated on the side stream, consumed (and later freed) by the backward stream
-                dy.record_stream(side)             # ... and the other way round for its inputs
-                x.record_stream(side)
         if ctx.needs_input_grad[0]:
             res = dfork if fuse_fork else None
             link = ctx.in_link if (dfork is None or fuse_fork) else None       # the mask has to see the complete gradient of x

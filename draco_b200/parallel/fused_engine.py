@@ -83,8 +83,14 @@ class FusedEngine:
                             and cfg.err_mode != "omniscient")
         self.push_stream = torch.cuda.Stream(device=device) if self.overlap_push else None
         ns = min(max(int(cfg.worker_streams), 1), len(self.local_workers))
+        # weight gradients on a side stream (auto = on: +5.6 % for a worker that owns its GPU, +2.4 % with seven workers sharing
+        # one).  The compute streams then get a higher priority than the side / push streams: the backward chain's CTAs are
+        # dispatched ahead of weight-gradient CTAs whenever both are pending
+        wgrad_side = (cfg.wgrad_stream in ("on", "auto") and bool(self.local_workers)
+                      and not cfg.profile_phases and cfg.zero_copy_grads)
+        prio = -1 if wgrad_side else 0
         # (compute stream, push stream) pairs; omniscient liars need the serial order, phase timers one timeline
-        self.worker_streams = ([(torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)) for _ in range(ns)]
+        self.worker_streams = ([(torch.cuda.Stream(device=device, priority=prio), torch.cuda.Stream(device=device)) for _ in range(ns)]
                                if ns > 1 and cfg.err_mode != "omniscient" and not cfg.profile_phases and not cfg.debug_checksum
                                else [])
         self.push_counters = torch.zeros(cfg.num_workers + 1, dtype=torch.int32, device=device)
@@ -95,8 +101,7 @@ class FusedEngine:
         self._staged_step = -1
         # one worker on this GPU (the 8-GPU topology): overlap the weight-gradient kernels with the rest of the backward chain
         from ..ops import conv as _conv_ops_mod
-        _conv_ops_mod.WGRAD_SIDE_STREAM = (cfg.wgrad_stream == "on" or (cfg.wgrad_stream == "auto" and len(self.local_workers) == 1)) \
-            and not cfg.profile_phases and cfg.zero_copy_grads      # stolen gradients only: see ops/conv.py
+        _conv_ops_mod.WGRAD_SIDE_STREAM = wgrad_side                 # stolen (zero-copy) gradients only: see ops/conv.py
 
         if cfg.deterministic:
             torch.backends.cudnn.deterministic = True
@@ -469,7 +474,12 @@ class FusedEngine:
         torch.cuda.synchronize()
         self._check_error()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # With the weight gradients on a side stream the step is captured on a HIGH-PRIORITY stream: whenever the backward chain
+        # (BatchNorm backward -> dgrad -> ...) and a weight-gradient / push kernel both have CTAs pending, the chain's are
+        # dispatched first (kernel-node priorities are captured from the stream).  Worker forward+backward 1.61 -> 1.52 ms.
+        from ..ops import conv as _conv_ops_mod
+        cap = torch.cuda.Stream(device=self.device, priority=-1) if _conv_ops_mod.WGRAD_SIDE_STREAM else None
+        with torch.cuda.graph(self.graph, stream=cap):
             self.kernels_per_step = self._enqueue_local_step(None)
         if self.local_workers and self.worker.zero_copy:
             # gradients allocated during capture live at fixed addresses of the graph's pool: publish them once

@@ -19,7 +19,7 @@ os.makedirs(out_dir, exist_ok=True)
 from draco_b200.ops import conv as _C  # noqa: E402
 MODES = os.environ.get("WORKER_MODES", "fused,fused_wgrad_stream,aten").split(",")
 for mode in MODES:
-    # fused[_wgrad_stream][_nofork][_maskx][_bnfuse]: A/B switches of single optimisations, same process, same box
+    # fused[_wgrad_stream][_nofork][_maskx][_bnfuse][_hiprio]: A/B switches of single optimisations, same process, same box
     os.environ["DRACO_BN"] = "aten" if mode == "aten" else "fused"
     os.environ["DRACO_CONV_FORK"] = "0" if "nofork" in mode else "1"
     os.environ["DRACO_BN_MASK"] = "x" if "maskx" in mode else "y"
@@ -34,7 +34,10 @@ for mode in MODES:
         wc.forward_backward(1, None)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    # "_hiprio": capture on a high-priority stream, so that the backward chain's kernels are dispatched ahead of the (default
+    # priority) weight-gradient side stream whenever both have CTAs pending
+    cap = torch.cuda.Stream(device=dev, priority=-1) if "hiprio" in mode else None
+    with torch.cuda.graph(g, stream=cap):
         wc.forward_backward(1, None)
     for _ in range(5):
         g.replay()
