@@ -68,6 +68,10 @@ class Trainer:
             if self.device.type == "cuda" and not cfg.data_on_device:
                 dataset.pin()
         self.dataset, self.test_set = dataset, test_set
+        # process-wide kernel switches owned by the fused engine: a later Trainer of another transport in the same process must not
+        # inherit them (weight gradients on a side stream need the fused engine's stolen gradients and joins)
+        from ..ops import conv as _conv_ops
+        _conv_ops.WGRAD_SIDE_STREAM = False
         if cfg.transport == "nvl" and self.device.type == "cuda":
             from .fused_engine import FusedEngine
             self.engine = FusedEngine(cfg, rank, world, self.device, dataset)
