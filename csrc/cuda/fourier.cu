@@ -8,7 +8,7 @@
 // Device formulation: (a) `cyclic_project_kernel`: one streaming pass over the complex64 arena R[n][D]
 // producing per-tile partials with fp64 accumulation, folded per tensor in a fixed order by `cyclic_fold_kernel`
 // (E[T][n]; no atomics -> the decode is bit-reproducible);
-// (b) `cyclic_locate_kernel`: one thread per tensor runs the shared fp64 locator core
+// (b) `cyclic_locate_kernel`: one CTA per tensor (lane 0 of one warp) runs the shared fp64 locator core
 // (csrc/common/locator_core.h) and emits v[T][n] as complex64; (c) the recombination Re(v^T R)/n is fused
 // with SGD + broadcast in aggregate_update.cu (mode 1).  No host round trip between (a), (b) and (c).
 #include "common.cuh"
@@ -99,9 +99,12 @@ struct LocateArgs {
   int* flagged;                   // [T] out number of rows flagged Byzantine
 };
 
-__global__ void cyclic_locate_kernel(const __grid_constant__ LocateArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.T) return;
+// One CTA per tensor: the locator is a serial O(n^3) fp64 computation per tensor, so the only parallelism is ACROSS tensors -- and
+// fp64 throughput per SM is tiny on this part, so the tensors are spread over as many SMs as there are tensors (62 CTAs for
+// ResNet-18) instead of sharing the fp64 pipe of two SMs (one warp per 32 tensors: 63 us in profiles/ncu_cyclic.md).
+__global__ void __launch_bounds__(32) cyclic_locate_kernel(const __grid_constant__ LocateArgs a) {
+  const int t = blockIdx.x;
+  if (threadIdx.x != 0 || t >= a.T) return;
   cplx E[DRC_LOC_MAX_N], v[DRC_LOC_MAX_N];
   for (int i = 0; i < a.n; ++i) {
     E[i] = c_make(a.E[((long long)t * a.n + i) * 2], a.E[((long long)t * a.n + i) * 2 + 1]);
@@ -117,7 +120,7 @@ __global__ void cyclic_locate_kernel(const __grid_constant__ LocateArgs a) {
 
 extern "C" int drc_cyclic_locate(const LocateArgs* args, cudaStream_t stream) {
   if (args->n > DRC_LOC_MAX_N || args->s > DRC_LOC_MAX_S) return (int)cudaErrorInvalidValue;
-  cyclic_locate_kernel<<<(args->T + 31) / 32, 32, 0, stream>>>(*args);
+  cyclic_locate_kernel<<<args->T, 32, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }
 
