@@ -66,6 +66,30 @@ def test_ops_fall_back_to_aten_on_cpu():
     assert {"features.0.weight", "features.1.running_var", "features.4.weight", "classifier.1.weight", "classifier.6.bias"} <= vkeys
 
 
+def test_fork_and_pool_fallbacks_on_cpu():
+    """``Conv2d(x, fork=True)`` (residual blocks: the shortcut's gradient is folded into the dgrad epilogue on the GPU path) and
+    ``global_avg_pool`` behave like the plain modules where the native kernels do not apply: same values, same gradients."""
+    from draco_b200.models.resnet import BasicBlock
+    from draco_b200.ops.pool import backend_counters, global_avg_pool
+    torch.manual_seed(1)
+    conv = Conv2d(8, 8, 3, padding=1, bias=False)
+    x = torch.randn(2, 8, 6, 6, requires_grad=True)
+    y, xf = conv(x, fork=True)
+    (y.sum() + (xf * 2.0).sum()).backward()
+    x2 = x.detach().clone().requires_grad_(True)
+    (F.conv2d(x2, conv.weight, padding=1).sum() + (x2 * 2.0).sum()).backward()
+    assert torch.allclose(x.grad, x2.grad, atol=1e-6)
+    blk = BasicBlock(8, 8, 1)
+    xb = torch.randn(2, 8, 6, 6, requires_grad=True)
+    out = blk(xb)
+    ref = F.relu(blk.bn2(blk.conv2(F.relu(blk.bn1(blk.conv1(xb))))) + xb)       # modules in training mode: same batch statistics
+    assert torch.allclose(out, ref, atol=1e-5)
+    before = backend_counters["aten"]
+    z = torch.randn(3, 16, 4, 4)
+    assert torch.allclose(global_avg_pool(z), F.avg_pool2d(z, 4).flatten(1), atol=1e-6)
+    assert backend_counters["aten"] == before + 1
+
+
 def test_profile_phases_reports_reference_timers(tmp_path, capsys):
     """--profile-phases: the reference's per-step timers (Comm / Comp / Encode on the worker, Method / Update on the PS)
     land in the JSONL records and in the human lines."""
